@@ -1,0 +1,92 @@
+"""ctypes binding of libddpmir.so (the C ABI declared in include/ddpmir.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every call checks the
+status code and raises with ddpmir_last_error().
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libddpmir.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_SIGMOID, ACT_SILU, ACT_GELU, ACT_TANH = range(7)
+IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
+
+
+class Epilogue(ctypes.Structure):
+    """Mirror of ddpmir_epilogue_t."""
+    _fields_ = [("bias", c_void_p), ("bias2", c_void_p), ("row_bias", c_void_p), ("img_scale", c_void_p),
+                ("mul", c_void_p), ("res", c_void_p), ("act", c_int), ("freq_mode", c_int), ("bs", c_int),
+                ("low", c_int)]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "ddpmir_version": (c_int, []),
+    "ddpmir_last_error": (c_char_p, []),
+    "ddpmir_ddrm_update": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                                   c_int, c_uint64, c_uint32, c_uint64, _P]),
+    "ddpmir_gmm_update": (c_int, [_P, _P, _P, _P, c_float, _P, _P, c_int64, c_int, c_float, c_int, c_uint64, c_uint32, _P]),
+    "ddpmir_lincomb": (c_int, [_P, c_float, _P, c_float, _P, c_float, _P, c_int64, c_uint64, c_uint32, _P]),
+    "ddpmir_philox_normal": (c_int, [_P, c_int64, c_uint64, c_uint32, _P]),
+    "ddpmir_quantize_u8_hwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_u8_hwc_to_nchw": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_phase_reference": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_phase_consistency": (c_int, [_P, _P, c_float, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_svd_lowrank": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),
+    "ddpmir_color_l1": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_time_embed": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "ddpmir_linear_rows": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
+    "ddpmir_groupnorm_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
+    "ddpmir_groupnorm_apply": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
+    "ddpmir_conv_input": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_conv3x3": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
+    "ddpmir_gemm": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
+    "ddpmir_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "ddpmir_block_transform": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ddpmir_maxpool2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_upsample2_concat": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_avgpool_pyramid": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_avif_combine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_out_conv_tanh": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
+    "ddpmir_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+}
+
+# not part of the public header: tuning hook used by tests/bench
+_PRIVATE = {"ddpmir_attention_set_expmode": (c_int, [c_int])}
+
+_lib = None
+
+
+class DdpmirError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise DdpmirError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (or `python -m ddpm_image_restoration_b200.build`). There is no CPU fallback.")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in {**_SIGNATURES, **_PRIVATE}.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ddpmir_last_error()
+        raise DdpmirError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,122 @@
+"""Host codec round trip -- the sampler's data-consistency operator (webp_inference.py:506-528,
+avif_inference.py:64-98, svd.ipynb#c1:L20-44).
+
+The codec itself stays Pillow's libwebp / libavif / libjpeg-turbo (bit-exactness with those libraries is the
+parity requirement), but around it the reference's serial per-image Python loop and fp32 transfers are replaced by
+  * on-device truncating uint8 quantisation + NCHW->HWC (ddpmir_quantize_u8_hwc), so only 1 byte/sample crosses PCIe,
+  * pinned staging buffers and asynchronous copies,
+  * a thread pool over images (Pillow releases the GIL inside encode/decode),
+  * raw uint8 decoder output consumed directly by the fused update kernel (ddpmir_ddrm_update, codec_u8_hwc=1).
+Unlike the reference's avif_compress there is no silent JPEG fallback: an AVIF failure raises.
+"""
+import concurrent.futures as cf
+import io
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+
+_POOL = None
+_POOL_THREADS = None
+
+
+def host_threads():
+    n = os.environ.get("DDPMIR_CODEC_THREADS")
+    if n:
+        return max(1, int(n))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
+def set_threads(n):
+    """Resize the codec thread pool (bench.py divides the host cores between ranks)."""
+    global _POOL, _POOL_THREADS
+    if _POOL is not None:
+        _POOL.shutdown(wait=True)
+    _POOL = cf.ThreadPoolExecutor(max_workers=max(1, int(n)), thread_name_prefix="ddpmir-codec")
+    _POOL_THREADS = max(1, int(n))
+
+
+def pool():
+    if _POOL is None:
+        set_threads(host_threads())
+    return _POOL
+
+
+def pool_threads():
+    pool()
+    return _POOL_THREADS
+
+
+def _clamp_quality(codec, quality):
+    q = int(quality)
+    return max(0, min(100, q)) if codec == "webp" else max(1, min(100, q))
+
+
+def _roundtrip_one(codec, q, src, dst):
+    """src, dst: [H, W, 3] uint8 numpy views (dst is written in place)."""
+    from PIL import Image
+    img = Image.fromarray(src, mode="RGB")
+    buf = io.BytesIO()
+    if codec == "webp":
+        img.save(buf, format="WEBP", quality=q)
+    elif codec == "avif":
+        img.save(buf, format="AVIF", quality=q)
+    elif codec == "jpeg":
+        img.save(buf, format="JPEG", quality=q, subsampling="4:4:4" if q > 30 else "4:2:0")
+    else:
+        raise ValueError(f"unknown codec {codec!r}")
+    buf.seek(0)
+    dec = Image.open(buf)
+    if dec.mode != "RGB":
+        dec = dec.convert("RGB")
+    dst[...] = np.asarray(dec, dtype=np.uint8)
+
+
+def submit_roundtrip(codec, quality, src_u8, dst_u8):
+    """Queue the round trip of every image of src_u8 [B,H,W,3] (numpy uint8) into dst_u8; returns the futures."""
+    q = _clamp_quality(codec, quality)
+    p = pool()
+    return [p.submit(_roundtrip_one, codec, q, src_u8[i], dst_u8[i]) for i in range(src_u8.shape[0])]
+
+
+def roundtrip_u8(codec, quality, src_u8):
+    dst = np.empty_like(src_u8)
+    for f in submit_roundtrip(codec, quality, src_u8, dst):
+        f.result()
+    return dst
+
+
+def _compress(x, quality, codec):
+    """Drop-in for {webp,avif,jpeg}_compress(x, quality): x in [-1,1], NCHW; returns fp32 on x's device."""
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("expected an [B,3,H,W] image batch")
+    if x.is_cuda:
+        u8 = ops.quantize_u8_hwc(x.contiguous().float())
+        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        dec = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        for f in submit_roundtrip(codec, quality, host.numpy(), dec.numpy()):
+            f.result()
+        return ops.u8_hwc_to_nchw(dec.to(x.device, non_blocking=True))
+    # host tensors: the whole operator is host work
+    u8 = (x.float() * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy()
+    dec = roundtrip_u8(codec, quality, u8)
+    return torch.from_numpy(dec).permute(0, 3, 1, 2).float().div(255.0).sub(0.5).mul(2.0)
+
+
+def webp_compress(x, quality):
+    return _compress(x, quality, "webp")
+
+
+def avif_compress(x, quality):
+    return _compress(x, quality, "avif")
+
+
+def jpeg_compress(x, quality):
+    return _compress(x, quality, "jpeg")

@@ -1,0 +1,349 @@
+// Fused (flash-style) self-attention for the UNet's full-resolution attention blocks: bf16 operands on the
+// tensor cores (mma.sync m16n8k16 / m16n8k8, fp32 accumulate), online softmax in registers, K/V tiles streamed
+// through shared memory with cp.async double buffering.  The L x L score matrix is never materialised
+// (the reference's nn.MultiheadAttention does, webp_inference.py:317-319, 68.7 GB per image at 256x256).
+//
+// With head_dim 8/16 this kernel is bound by the exp (MUFU) and FMA pipes, not by the tensor pipe: one 16x64
+// score tile costs 16 HMMA but 1024 exp2 + ~3 FP32 ops per score.  Hence the design choices below:
+//   * softmax scale folded into one FFMA per score (exp2 domain), row sums taken by the tensor core
+//     (P times a constant ones-column fragment) instead of 1 FADD per score,
+//   * optional packed bf16x2 exp2 (EXPMODE 1): two scores per MUFU op,
+//   * P stays in registers as the A operand of the PV product (no shared-memory round trip).
+#include "common.cuh"
+
+namespace {
+
+constexpr int KT = 64;  // keys per shared-memory tile
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+// D += A(16x16) * B(16x8)
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// D += A(16x8) * B(8x8)
+__device__ __forceinline__ void mma_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.ftz.bf16x2 %0, %1;\n" : "=r"(y) : "r"(x));
+    return y;
+}
+
+// swizzle of 16-byte chunks inside a row of CPR chunks so that 8 consecutive rows x one logical chunk hit
+// 8 distinct 16-byte bank groups (conflict-free ldmatrix)
+template <int CPR> __device__ __forceinline__ int swz(int row, int chunk) {
+    if (CPR == 1) return chunk;
+    constexpr int DIV = (8 / CPR) > 1 ? (8 / CPR) : 1;
+    constexpr int MOD = CPR < 8 ? CPR : 8;
+    return chunk ^ ((row / DIV) % MOD);
+}
+
+template <int HD, int MT, int NWARPS, int EXPMODE>
+__global__ void __launch_bounds__(NWARPS * 32)
+attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, float scale_log2) {
+    constexpr int CPR = HD / 8;            // 16-byte chunks per K/V row
+    constexpr int NT = NWARPS * 32;
+    constexpr int ROWS = NWARPS * MT * 16;  // query rows per CTA
+    constexpr int NDT = HD / 8;            // 8-wide output column tiles
+    constexpr int KSTEPS = HD >= 16 ? HD / 16 : 1;
+    constexpr int TILE_ELEMS = KT * HD;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    bf16* Ks = reinterpret_cast<bf16*>(smem_raw);              // [2][KT][HD]
+    bf16* Vs = Ks + 2 * TILE_ELEMS;                            // [2][KT][HD]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const long long rstride = 3LL * C;
+    const bf16* qbase = qkv + (long long)b * L * rstride + (long long)h * HD;
+    const bf16* kbase = qbase + C;
+    const bf16* vbase = qbase + 2 * C;
+
+    auto load_tile = [&](int t, int stage) {
+        const int k0 = t * KT;
+        bf16* kd = Ks + stage * TILE_ELEMS;
+        bf16* vd = Vs + stage * TILE_ELEMS;
+        for (int i = tid; i < KT * CPR; i += NT) {
+            const int row = i / CPR, ch = i - row * CPR;
+            const long long g = (long long)(k0 + row) * rstride + ch * 8;
+            const int so = row * HD + swz<CPR>(row, ch) * 8;
+            cp_async16(kd + so, kbase + g);
+            cp_async16(vd + so, vbase + g);
+        }
+    };
+
+    // ---- Q fragments straight from global memory (A operand layout) ------------------------------------
+    const int r_lo = lane >> 2, c_lo = (lane & 3) * 2;
+    uint32_t qf[MT][KSTEPS][4];
+    const int row0 = blockIdx.x * ROWS + warp * (MT * 16);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int ra = row0 + mt * 16 + r_lo, rb = ra + 8;
+        const bf16* pa = qbase + (long long)(ra < L ? ra : L - 1) * rstride;
+        const bf16* pb = qbase + (long long)(rb < L ? rb : L - 1) * rstride;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            qf[mt][ks][0] = *reinterpret_cast<const uint32_t*>(pa + ks * 16 + c_lo);
+            qf[mt][ks][1] = *reinterpret_cast<const uint32_t*>(pb + ks * 16 + c_lo);
+            if (HD >= 16) {
+                qf[mt][ks][2] = *reinterpret_cast<const uint32_t*>(pa + ks * 16 + 8 + c_lo);
+                qf[mt][ks][3] = *reinterpret_cast<const uint32_t*>(pb + ks * 16 + 8 + c_lo);
+            } else {
+                qf[mt][ks][2] = 0u; qf[mt][ks][3] = 0u;
+            }
+        }
+    }
+
+    float o[MT][NDT][4];
+    float ls[MT][4];
+    float mrow[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int dt = 0; dt < NDT; ++dt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[mt][dt][i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ls[mt][i] = 0.f;
+        mrow[mt][0] = -INFINITY; mrow[mt][1] = -INFINITY;
+    }
+    const uint32_t ones = (lane >> 2) == 0 ? 0x3F803F80u : 0u;  // B fragment of a ones column at n = 0
+
+    const int ntiles = L / KT;
+    load_tile(0, 0);
+    cp_async_commit();
+
+    const uint32_t ks_s = (uint32_t)__cvta_generic_to_shared(Ks);
+    const uint32_t vs_s = (uint32_t)__cvta_generic_to_shared(Vs);
+    const int lrow = lane & 7, lmat = lane >> 3;
+
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) {
+            load_tile(t + 1, (t + 1) & 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const uint32_t kst = ks_s + (t & 1) * TILE_ELEMS * 2;
+        const uint32_t vst = vs_s + (t & 1) * TILE_ELEMS * 2;
+
+        // ---- S = Q K^T ----------------------------------------------------------------------------------
+        float s[MT][8][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[mt][nt][i] = 0.f;
+
+        if (HD >= 16) {
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {  // n-tile pairs
+                    const int row = (2 * p + (lmat >> 1)) * 8 + lrow;
+                    const int ch = 2 * ks + (lmat & 1);
+                    uint32_t kf[4];
+                    ldsm_x4(kf, kst + (row * HD + swz<CPR>(row, ch) * 8) * 2);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_16816(s[mt][2 * p], qf[mt][ks], kf[0], kf[1]);
+                        mma_16816(s[mt][2 * p + 1], qf[mt][ks], kf[2], kf[3]);
+                    }
+                }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {  // four n-tiles per ldmatrix.x4 (rows are 16 B)
+                const int row = (4 * p + lmat) * 8 + lrow;
+                uint32_t kf[4];
+                ldsm_x4(kf, kst + row * HD * 2);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) mma_1688(s[mt][4 * p + q], qf[mt][0][0], qf[mt][0][1], kf[q]);
+            }
+        }
+
+        // ---- online softmax (exp2 domain), P packed to bf16 as the A operand of PV ------------------------
+        uint32_t pf[MT][4][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            float mx0 = s[mt][0][0], mx1 = s[mt][0][2];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(mrow[mt][0], mx0 * scale_log2);
+            const float mn1 = fmaxf(mrow[mt][1], mx1 * scale_log2);
+            const float c0 = ex2f(mrow[mt][0] - mn0), c1 = ex2f(mrow[mt][1] - mn1);
+            mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+#pragma unroll
+            for (int dt = 0; dt < NDT; ++dt) {
+                o[mt][dt][0] *= c0; o[mt][dt][1] *= c0; o[mt][dt][2] *= c1; o[mt][dt][3] *= c1;
+            }
+            ls[mt][0] *= c0; ls[mt][1] *= c0; ls[mt][2] *= c1; ls[mt][3] *= c1;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float x0 = fmaf(s[mt][nt][0], scale_log2, -mn0), x1 = fmaf(s[mt][nt][1], scale_log2, -mn0);
+                const float x2 = fmaf(s[mt][nt][2], scale_log2, -mn1), x3 = fmaf(s[mt][nt][3], scale_log2, -mn1);
+                uint32_t p01, p23;
+                if (EXPMODE == 1) {
+                    p01 = ex2_bf16x2(pack_bf16(x0, x1));
+                    p23 = ex2_bf16x2(pack_bf16(x2, x3));
+                } else {
+                    p01 = pack_bf16(ex2f(x0), ex2f(x1));
+                    p23 = pack_bf16(ex2f(x2), ex2f(x3));
+                }
+                pf[mt][nt >> 1][(nt & 1) * 2 + 0] = p01;
+                pf[mt][nt >> 1][(nt & 1) * 2 + 1] = p23;
+            }
+        }
+
+        // ---- O += P V ; row sums += P 1 ---------------------------------------------------------------------
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma_16816(ls[mt], pf[mt][kk], ones, ones);
+            if (HD >= 16) {
+#pragma unroll
+                for (int a = 0; a < NDT / 2; ++a) {
+                    const int row = kk * 16 + (lmat & 1) * 8 + lrow;
+                    const int ch = 2 * a + (lmat >> 1);
+                    uint32_t vf[4];
+                    ldsm_x4_t(vf, vst + (row * HD + swz<CPR>(row, ch) * 8) * 2);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_16816(o[mt][2 * a], pf[mt][kk], vf[0], vf[1]);
+                        mma_16816(o[mt][2 * a + 1], pf[mt][kk], vf[2], vf[3]);
+                    }
+                }
+            } else {
+                const int row = kk * 16 + (lmat & 1) * 8 + lrow;
+                uint32_t vf[2];
+                ldsm_x2_t(vf, vst + row * HD * 2);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma_16816(o[mt][0], pf[mt][kk], vf[0], vf[1]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- normalise and store --------------------------------------------------------------------------------
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const float l0 = __shfl_sync(0xffffffffu, ls[mt][0], lane & ~3);
+        const float l1 = __shfl_sync(0xffffffffu, ls[mt][2], lane & ~3);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        const int ra = row0 + mt * 16 + r_lo, rb = ra + 8;
+        bf16* oa = out + ((long long)b * L + ra) * C + (long long)h * HD + c_lo;
+        bf16* ob = out + ((long long)b * L + rb) * C + (long long)h * HD + c_lo;
+#pragma unroll
+        for (int dt = 0; dt < NDT; ++dt) {
+            if (ra < L) *reinterpret_cast<uint32_t*>(oa + dt * 8) = pack_bf16(o[mt][dt][0] * i0, o[mt][dt][1] * i0);
+            if (rb < L) *reinterpret_cast<uint32_t*>(ob + dt * 8) = pack_bf16(o[mt][dt][2] * i1, o[mt][dt][3] * i1);
+        }
+    }
+}
+
+template <int HD, int MT, int NWARPS, int EXPMODE>
+int launch(const void* qkv, void* out, int B, int L, int C, int heads, cudaStream_t st) {
+    constexpr int ROWS = NWARPS * MT * 16;
+    const size_t smem = (size_t)4 * KT * HD * sizeof(bf16);
+    auto kern = attn_mma_kernel<HD, MT, NWARPS, EXPMODE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { ddpmir_set_error("attention: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
+    }
+    const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+    dim3 grid(ceil_div(L, ROWS), heads, B);
+    kern<<<grid, NWARPS * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, L, C, scale_log2);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+int g_expmode = 0;
+
+}  // namespace
+
+// test / tuning hook: 0 = fp32 ex2 per score, 1 = packed bf16x2 ex2
+extern "C" int ddpmir_attention_set_expmode(int mode) {
+    g_expmode = mode ? 1 : 0;
+    return DDPMIR_OK;
+}
+
+int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, cudaStream_t st);
+
+int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, cudaStream_t st) {
+    const int hd = C / heads;
+    if (L % KT != 0) return DDPMIR_ERR_UNSUPPORTED;
+#define GO(HD, MT, NW) (g_expmode ? launch<HD, MT, NW, 1>(qkv, out, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, B, L, C, heads, st))
+    switch (hd) {
+        case 8: return GO(8, 1, 8);
+        case 16: return GO(16, 1, 8);
+        case 32: return GO(32, 1, 8);
+        case 64: return GO(64, 1, 4);
+        case 128: return GO(128, 1, 4);
+        default: return DDPMIR_ERR_UNSUPPORTED;
+    }
+#undef GO
+}
+
+extern "C" int ddpmir_attention(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, int impl,
+                                ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(qkv && out, "attention: null pointer");
+    DDPMIR_CHECK_ARG(B > 0 && L > 0 && heads > 0 && C % heads == 0 && (C / heads) % 8 == 0, "attention: bad shape");
+    DDPMIR_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DDPMIR_BF16 && impl != DDPMIR_IMPL_SIMT) {
+        int rc = ddpmir_attention_mma(qkv, B, L, C, heads, out, st);
+        if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
+        if (impl == DDPMIR_IMPL_TENSOR) {
+            ddpmir_set_error("attention: tensor-core kernel needs L %% 64 == 0 and head_dim in {8,16,32,64,128}");
+            return rc;
+        }
+    } else if (impl == DDPMIR_IMPL_TENSOR) {
+        ddpmir_set_error("attention: tensor-core kernel is bf16 only");
+        return DDPMIR_ERR_UNSUPPORTED;
+    }
+    return ddpmir_attention_simt(qkv, dtype, B, L, C, heads, out, st);
+}

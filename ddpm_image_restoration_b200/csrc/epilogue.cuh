@@ -1,0 +1,80 @@
+// Epilogue shared by every GEMM-shaped kernel (SIMT and tensor-core): see ddpmir_epilogue_t in ddpmir.h.
+#pragma once
+#include "common.cuh"
+
+struct EpiDev {
+    const float* bias;
+    const float* bias2;
+    const float* row_bias;
+    const float* img_scale;
+    const void* mul;
+    const void* res;
+    int act;
+    int freq_mode;
+    int bs;
+    int low;
+    int H, W, N;
+};
+
+static inline EpiDev make_epi(const ddpmir_epilogue_t* e, int H, int W, int N) {
+    EpiDev d;
+    d.bias = e ? e->bias : nullptr;
+    d.bias2 = e ? e->bias2 : nullptr;
+    d.row_bias = e ? e->row_bias : nullptr;
+    d.img_scale = e ? e->img_scale : nullptr;
+    d.mul = e ? e->mul : nullptr;
+    d.res = e ? e->res : nullptr;
+    d.act = e ? e->act : 0;
+    d.freq_mode = e ? e->freq_mode : 0;
+    d.bs = e ? e->bs : 0;
+    d.low = e ? e->low : 0;
+    d.H = H; d.W = W; d.N = N;
+    return d;
+}
+
+static inline int check_epi(const ddpmir_epilogue_t* e, int N) {
+    if (!e) return DDPMIR_OK;
+    if (e->freq_mode < 0 || e->freq_mode > 2) { ddpmir_set_error("epilogue: freq_mode %d", e->freq_mode); return DDPMIR_ERR_INVALID; }
+    if (e->freq_mode && (e->bs <= 0 || e->low <= 0)) { ddpmir_set_error("epilogue: freq_mode needs bs/low"); return DDPMIR_ERR_INVALID; }
+    if (e->freq_mode == 1 && (N & 1)) { ddpmir_set_error("epilogue: freq_mode 1 needs even N"); return DDPMIR_ERR_INVALID; }
+    if (e->freq_mode == 2 && (!e->bias2 || !e->bias)) { ddpmir_set_error("epilogue: freq_mode 2 needs bias and bias2"); return DDPMIR_ERR_INVALID; }
+    return DDPMIR_OK;
+}
+
+// Per-row (pixel) context, computed once per output row.
+struct EpiRow {
+    int b;
+    bool low;
+    float scale;  // per-image scale to apply (already resolved for freq_mode 2)
+};
+
+__device__ __forceinline__ EpiRow epi_row(const EpiDev& p, long long m) {
+    EpiRow r;
+    const int hw = p.H * p.W;
+    r.b = (int)(m / hw);
+    r.low = false;
+    if (p.freq_mode) {
+        const int rem = (int)(m - (long long)r.b * hw);
+        const int h = rem / p.W, w = rem - h * p.W;
+        r.low = is_low_freq(h, w, p.H, p.W, p.bs, p.low);
+    }
+    r.scale = p.img_scale ? p.img_scale[r.b] : 1.f;
+    if (p.freq_mode == 2 && r.low) r.scale = 1.f;
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ float epi_apply(const EpiDev& p, const EpiRow& r, float acc, long long m, int n) {
+    float v = acc;
+    if (p.freq_mode == 2 && !r.low) v += p.bias2[n];
+    else if (p.bias) v += p.bias[n];
+    if (p.row_bias) v += p.row_bias[(long long)r.b * p.N + n];
+    v = act_apply(p.act, v);
+    if (p.freq_mode == 1) {
+        if ((n < (p.N >> 1)) != r.low) v = 0.f;
+    }
+    v *= r.scale;
+    if (p.mul) v *= to_f(reinterpret_cast<const T*>(p.mul)[m * p.N + n]);
+    if (p.res) v += to_f(reinterpret_cast<const T*>(p.res)[m * p.N + n]);
+    return v;
+}

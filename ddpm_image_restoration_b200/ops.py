@@ -1,0 +1,286 @@
+"""Tensor-level wrappers over the C ABI (ddpmir.h).  PyTorch is used for device memory and streams only:
+every function takes CUDA tensors, allocates its outputs/workspaces with torch.empty and enqueues the kernels
+on torch's current stream.  There is no CPU path -- CPU tensors raise."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, BF16, F32,  # noqa: F401
+                   IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR, Epilogue)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.DdpmirError("ddpmir ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.DdpmirError("ddpmir ops need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise _lib.DdpmirError(f"unsupported activation dtype {dtype}")
+
+
+def _f32(t, name):
+    if t is not None and t.dtype != torch.float32:
+        raise _lib.DdpmirError(f"{name} must be float32")
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sampler-level
+# ---------------------------------------------------------------------------------------------------------
+def ddrm_update(x_theta, codec, y, t, sigma_scale, eta=0.85, eta_b=1.0, z=None, last_step=False, seed=0, step=0,
+                out=None, noise_offset=0):
+    """codec: fp32 NCHW tensor or uint8 [B,H,W,C] tensor (raw decoder pixels)."""
+    B, C, H, W = x_theta.shape
+    _f32(x_theta, "x_theta"); _f32(y, "y"); _f32(t, "t"); _f32(z, "z")
+    u8 = codec.dtype == torch.uint8
+    if not u8:
+        _f32(codec, "codec")
+    out = torch.empty_like(x_theta) if out is None else out
+    rc = _lib.lib().ddpmir_ddrm_update(_p(x_theta), _p(codec), int(u8), _p(y), _p(z), _p(t), _p(out), B, C, H, W,
+                                       float(sigma_scale), float(eta), float(eta_b), int(last_step), int(seed),
+                                       int(step), int(noise_offset), _stream())
+    _lib.check(rc, "ddrm_update")
+    return out
+
+
+def gmm_update(x_t, pred, y=None, svd_prior=None, g=0.0, z=None, use_first=True, noise_scale=0.0, last_step=False,
+               seed=0, step=0):
+    out = torch.empty_like(x_t)
+    rc = _lib.lib().ddpmir_gmm_update(_p(x_t), _p(pred), _p(y), _p(svd_prior), float(g), _p(z), _p(out), x_t.numel(),
+                                      int(use_first), float(noise_scale), int(last_step), int(seed), int(step), _stream())
+    _lib.check(rc, "gmm_update")
+    return out
+
+
+def lincomb(a, wa, b=None, wb=0.0, z=None, sigma=0.0, seed=0, step=0):
+    out = torch.empty_like(a)
+    rc = _lib.lib().ddpmir_lincomb(_p(a), float(wa), _p(b), float(wb), _p(z), float(sigma), _p(out), a.numel(), int(seed),
+                                   int(step), _stream())
+    _lib.check(rc, "lincomb")
+    return out
+
+
+def philox_normal(shape, seed, step, device="cuda"):
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().ddpmir_philox_normal(_p(out), out.numel(), int(seed), int(step), _stream()), "philox_normal")
+    return out
+
+
+def u8_hwc_to_nchw(u8):
+    """ToTensor + sub(0.5).mul(2.0) of raw decoder pixels: uint8 [B,H,W,C] -> fp32 [B,C,H,W]."""
+    B, H, W, C = u8.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=u8.device)
+    _lib.check(_lib.lib().ddpmir_u8_hwc_to_nchw(_p(u8), _p(out), B, C, H, W, _stream()), "u8_hwc_to_nchw")
+    return out
+
+
+def quantize_u8_hwc(x, out=None):
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device) if out is None else out
+    _lib.check(_lib.lib().ddpmir_quantize_u8_hwc(_p(_f32(x, "x")), _p(out), B, C, H, W, _stream()), "quantize_u8_hwc")
+    return out
+
+
+def phase_reference(ref):
+    B, C, H, W = ref.shape
+    phasor = torch.empty((B * C, H, W, 2), dtype=torch.float32, device=ref.device)
+    ws = torch.empty_like(phasor)
+    _lib.check(_lib.lib().ddpmir_phase_reference(_p(_f32(ref, "ref")), B * C, H, W, _p(phasor), _p(ws), _stream()),
+               "phase_reference")
+    return phasor
+
+
+def phase_consistency_cached(x, phasor, alpha):
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    ws = torch.empty((B * C, H, W, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ddpmir_phase_consistency(_p(_f32(x, "x")), _p(phasor), float(alpha), B * C, H, W, _p(out), _p(ws),
+                                                   _stream()), "phase_consistency")
+    return out
+
+
+def svd_lowrank(x, k, sweeps=0):
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    ws = torch.empty((B * C * (H * W + 2 * H),), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ddpmir_svd_lowrank(_p(_f32(x, "x")), B * C, H, W, int(k), _p(out), _p(ws), int(sweeps), _stream()),
+               "svd_lowrank")
+    return out
+
+
+def color_l1(pred, target):
+    B, C, H, W = pred.shape
+    if C != 3:
+        raise _lib.DdpmirError("color_l1 needs 3-channel images")
+    out = torch.empty((1,), dtype=torch.float32, device=pred.device)
+    ws = torch.empty((3,), dtype=torch.float64, device=pred.device)
+    _lib.check(_lib.lib().ddpmir_color_l1(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B, H, W, _p(out), _p(ws),
+                                          _stream()), "color_l1")
+    return out[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# UNet-level (NHWC activations)
+# ---------------------------------------------------------------------------------------------------------
+def time_embed(t, w0, b0, w1, b1):
+    B, dim = t.shape[0], w1.shape[0]
+    ws = torch.empty((B * 5 * dim,), dtype=torch.float32, device=t.device)
+    out = torch.empty((B, dim), dtype=torch.float32, device=t.device)
+    _lib.check(_lib.lib().ddpmir_time_embed(_p(_f32(t, "t")), B, dim, _p(w0), _p(b0), _p(w1), _p(b1), _p(ws), _p(out),
+                                            _stream()), "time_embed")
+    return out
+
+
+def linear_rows(x, w, bias, act=ACT_NONE, out=None):
+    rows, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((rows, N), dtype=torch.float32, device=x.device)
+    elif out.numel() != rows * N or out.dtype != torch.float32:
+        raise _lib.DdpmirError("linear_rows: bad out tensor")
+    _lib.check(_lib.lib().ddpmir_linear_rows(_p(_f32(x, "x")), rows, K, _p(_f32(w, "w")), _p(bias), N, act, _p(out),
+                                             _stream()), "linear_rows")
+    return out
+
+
+def groupnorm_stats(x, groups, eps=1e-5, nchw=False):
+    if nchw:
+        B, C, H, W = x.shape
+        HW = H * W
+    else:
+        B, H, W, C = x.shape
+        HW = H * W
+    mr = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
+    ws = torch.empty((B * groups * 2,), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.lib().ddpmir_groupnorm_stats(_p(x), _code(x.dtype), int(nchw), B, HW, C, groups, float(eps), _p(mr),
+                                                 _p(ws), _stream()), "groupnorm_stats")
+    return mr
+
+
+def groupnorm_apply(x, mean_rstd, gamma, beta, act=ACT_NONE):
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().ddpmir_groupnorm_apply(_p(x), _code(x.dtype), B, H * W, C, mean_rstd.shape[1], _p(mean_rstd),
+                                                 _p(gamma), _p(beta), act, _p(out), _stream()), "groupnorm_apply")
+    return out
+
+
+def conv_input(x, w, bias, out_dtype, mean_rstd=None, gamma=None, beta=None, row_bias=None):
+    B, Cin, H, W = x.shape
+    N, ks = w.shape[0], w.shape[-1]
+    out = torch.empty((B, H, W, N), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.lib().ddpmir_conv_input(_p(_f32(x, "x")), B, Cin, H, W, _p(mean_rstd), _p(gamma), _p(beta), _p(_f32(w, "w")),
+                                            _p(bias), _p(row_bias), N, ks, _code(out_dtype), _p(out), _stream()),
+               "conv_input")
+    return out
+
+
+def _epi(bias=None, bias2=None, row_bias=None, img_scale=None, mul=None, res=None, act=ACT_NONE, freq_mode=0, bs=0, low=0):
+    def a(t):
+        return None if t is None else t.data_ptr()
+    for t in (bias, bias2, row_bias, img_scale, mul, res):
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise _lib.DdpmirError("epilogue tensors must be contiguous CUDA tensors")
+    return Epilogue(a(bias), a(bias2), a(row_bias), a(img_scale), a(mul), a(res), act, freq_mode, bs, low)
+
+
+def conv3x3(x, w, N, impl=IMPL_AUTO, **epi):
+    """x [B,H,W,Cin]; w packed [N, 9*Cin] (kh,kw,cin) in x.dtype."""
+    B, H, W, Cin = x.shape
+    if w.dtype != x.dtype or w.numel() != N * 9 * Cin:
+        raise _lib.DdpmirError("conv3x3: weight must be packed [N, 9*Cin] in the activation dtype")
+    out = torch.empty((B, H, W, N), dtype=x.dtype, device=x.device)
+    e = _epi(**epi)
+    _lib.check(_lib.lib().ddpmir_conv3x3(_p(x), _code(x.dtype), B, H, W, Cin, _p(w), N, ctypes.byref(e), _p(out), impl,
+                                         _stream()), "conv3x3")
+    return out
+
+
+def gemm(x, w, N, impl=IMPL_AUTO, **epi):
+    """x [B,H,W,K]; w [N,K] in x.dtype."""
+    B, H, W, K = x.shape
+    if w.dtype != x.dtype or w.numel() != N * K:
+        raise _lib.DdpmirError("gemm: weight must be [N, K] in the activation dtype")
+    out = torch.empty((B, H, W, N), dtype=x.dtype, device=x.device)
+    e = _epi(**epi)
+    _lib.check(_lib.lib().ddpmir_gemm(_p(x), _code(x.dtype), B, H, W, K, _p(w), N, ctypes.byref(e), _p(out), impl, _stream()),
+               "gemm")
+    return out
+
+
+def attention(qkv, heads, impl=IMPL_AUTO):
+    """qkv [B, L, 3C] -> [B, L, C]."""
+    B, L, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)
+    _lib.check(_lib.lib().ddpmir_attention(_p(qkv), _code(qkv.dtype), B, L, C, heads, _p(out), impl, _stream()), "attention")
+    return out
+
+
+def block_transform(x, T, alpha=0.0, beta=1.0):
+    B, H, W, C = x.shape
+    bs = T.shape[-1]
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().ddpmir_block_transform(_p(x), _code(x.dtype), B, H, W, C, _p(_f32(T, "T")), bs, int(T.dim() == 3),
+                                                 float(alpha), float(beta), _p(out), _stream()), "block_transform")
+    return out
+
+
+def maxpool2(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().ddpmir_maxpool2(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "maxpool2")
+    return out
+
+
+def upsample2_concat(lo, skip):
+    B, H, W, C1 = lo.shape
+    C2 = skip.shape[-1]
+    out = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=lo.dtype, device=lo.device)
+    _lib.check(_lib.lib().ddpmir_upsample2_concat(_p(lo), _p(skip), _code(lo.dtype), B, H, W, C1, C2, _p(out), _stream()),
+               "upsample2_concat")
+    return out
+
+
+def avgpool_pyramid(x):
+    B, H, W, C = x.shape
+    out = torch.empty((85, B, C), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ddpmir_avgpool_pyramid(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "avgpool_pyramid")
+    return out
+
+
+def avif_combine(h, xt, gates, color, edge):
+    B, H, W, C = h.shape
+    out = torch.empty_like(h)
+    _lib.check(_lib.lib().ddpmir_avif_combine(_p(h), _p(xt), _p(_f32(gates, "gates")), _p(color), _p(edge), _code(h.dtype), B, H,
+                                              W, C, _p(out), _stream()), "avif_combine")
+    return out
+
+
+def out_conv_tanh(x, w, bias):
+    B, H, W, Cin = x.shape
+    N = w.shape[0]
+    out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().ddpmir_out_conv_tanh(_p(x), _code(x.dtype), B, H, W, Cin, _p(_f32(w, "w")), _p(bias), N, _p(out),
+                                               _stream()), "out_conv_tanh")
+    return out
+
+
+def cast_bf16(x):
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().ddpmir_cast_f32_to_bf16(_p(_f32(x, "x")), _p(out), x.numel(), _stream()), "cast_bf16")
+    return out

@@ -1,0 +1,170 @@
+"""Samplers with the reference's API:
+
+  DDRMWebPSampler / DDRMAVIFSampler / DDRMJPEGSampler(model).sample(x_t, quality, steps=100, eta=0.85, eta_b=1.0)
+      webp_inference.py:553-602, avif_inference.py:410-459, svd.ipynb#c1:L336-385
+  GaussianMixtureSampler(model, num_timesteps=100).sample(x_t, steps=100, use_phase_consistency=True,
+      use_svd_guide=True, guidance_scale=1.0)                          0409_method.ipynb#c1:L390-449
+
+Per timestep the reference runs the UNet, a serial host codec loop with fp32 transfers, ~8 element-wise kernels and
+a Philox kernel.  Here one step is: UNet forward (libddpmir kernels) -> on-device uint8 quantisation -> pinned D2H ->
+thread-pooled codec -> pinned H2D of raw pixels -> ONE fused update kernel (codec dequantisation, data-consistency,
+eta mixing, in-kernel Philox noise) -> optional phase-consistency FFT kernels.  The batch is split into micro-batches
+so the host codec of one micro-batch overlaps the UNet of the next.
+
+Noise: by default generated in-kernel (Philox4x32-10 keyed by seed/step/element -- reproducible, independent of launch
+geometry).  For parity runs pass `noise_fn(i, like) -> tensor` (and `coin_fn(i) -> float` for the GMM sampler), which
+replaces torch.randn_like / torch.rand(1) of the reference.
+"""
+import torch
+
+from . import codec as _codec
+from . import ops
+
+_DDRM = {
+    "webp": dict(codec="webp", sigma=0.2, q_thr=15, period=5, alpha=0.7),   # webp_inference.py:588,595-597
+    "jpeg": dict(codec="jpeg", sigma=0.2, q_thr=20, period=5, alpha=0.7),   # svd.ipynb#c1:L371,378-380
+    "avif": dict(codec="avif", sigma=0.15, q_thr=30, period=3, alpha=0.8),  # avif_inference.py:445,452-454
+}
+
+
+class _DDRMSampler:
+    family = None
+
+    def __init__(self, model, seed=0, micro_batches=None, noise_fn=None):
+        self.model = model
+        self.seed = seed
+        self.micro_batches = micro_batches
+        self.noise_fn = noise_fn
+        self.last_stats = {}
+
+    def _chunks(self, B):
+        n = self.micro_batches
+        if n is None:
+            n = 4 if B >= 16 else (2 if B >= 4 else 1)
+        n = max(1, min(n, B))
+        size = (B + n - 1) // n
+        return [(s, min(B, s + size)) for s in range(0, B, size)]
+
+    def sample(self, x_t, quality, steps=100, eta=0.85, eta_b=1.0):
+        cfg = _DDRM[self.family]
+        if not x_t.is_cuda:
+            raise RuntimeError("the B200 sampler runs on CUDA only (no CPU fallback)")
+        self.model.eval()
+        dev = x_t.device
+        x_t = x_t.contiguous().float().clone()
+        y = x_t.clone()
+        B, C, H, W = x_t.shape
+        chunks = self._chunks(B)
+        use_phase = quality < cfg["q_thr"]
+        phasor = ops.phase_reference(y) if (use_phase and steps > cfg["period"]) else None
+        # staging: device uint8 buffers and pinned host buffers, one set per micro-batch
+        dev_u8 = [torch.empty((e - s, H, W, C), dtype=torch.uint8, device=dev) for s, e in chunks]
+        pin_src = [torch.empty((e - s, H, W, C), dtype=torch.uint8, pin_memory=True) for s, e in chunks]
+        pin_dst = [torch.empty((e - s, H, W, C), dtype=torch.uint8, pin_memory=True) for s, e in chunks]
+        dev_dec = [torch.empty((e - s, H, W, C), dtype=torch.uint8, device=dev) for s, e in chunks]
+        events = [torch.cuda.Event() for _ in chunks]
+        h2d = d2h = 0
+        with torch.no_grad():
+            for i in range(steps - 1, -1, -1):
+                t_val = float(i) / steps
+                x_next = torch.empty_like(x_t)
+                thetas = []
+                # phase 1: enqueue all GPU work of this timestep (UNet + quantise + D2H) per micro-batch
+                for k, (s, e) in enumerate(chunks):
+                    t = torch.full((e - s,), t_val, dtype=torch.float32, device=dev)
+                    x_theta = self.model(x_t[s:e], t, t)
+                    ops.quantize_u8_hwc(x_theta, out=dev_u8[k])
+                    pin_src[k].copy_(dev_u8[k], non_blocking=True)
+                    events[k].record()
+                    thetas.append((x_theta, t))
+                    d2h += dev_u8[k].numel()
+                # phase 2: as each micro-batch lands on the host, fan its images out to the codec pool
+                futures = []
+                for k in range(len(chunks)):
+                    events[k].synchronize()
+                    futures.append(_codec.submit_roundtrip(cfg["codec"], quality, pin_src[k].numpy(), pin_dst[k].numpy()))
+                # phase 3: decoded pixels back to the device, fused update
+                for k, (s, e) in enumerate(chunks):
+                    for f in futures[k]:
+                        f.result()
+                    dev_dec[k].copy_(pin_dst[k], non_blocking=True)
+                    h2d += pin_dst[k].numel()
+                    x_theta, t = thetas[k]
+                    z = None
+                    if self.noise_fn is not None and i > 0:
+                        z = self.noise_fn(i, x_t)[s:e].contiguous()
+                    # the flat NCHW element index inside the FULL batch keys the noise (noise_offset), so the result
+                    # does not depend on the micro-batch split
+                    ops.ddrm_update(x_theta, dev_dec[k], y[s:e], t, cfg["sigma"], eta, eta_b, z=z, last_step=(i == 0),
+                                    seed=self.seed, step=i, out=x_next[s:e], noise_offset=s * C * H * W)
+                x_t = x_next
+                if i > 0 and use_phase and i % cfg["period"] == 0:
+                    x_t = ops.phase_consistency_cached(x_t, phasor, cfg["alpha"])
+        self.last_stats = dict(h2d_bytes=h2d, d2h_bytes=d2h, steps=steps, micro_batches=len(chunks),
+                               codec_threads=_codec.pool_threads())
+        return x_t
+
+
+class DDRMWebPSampler(_DDRMSampler):
+    family = "webp"
+
+
+class DDRMJPEGSampler(_DDRMSampler):
+    family = "jpeg"
+
+
+class DDRMAVIFSampler(_DDRMSampler):
+    family = "avif"
+
+
+def phase_consistency(x, ref, alpha=0.7):
+    """Drop-in for phase_consistency(x, ref, alpha), webp_inference.py:531-550."""
+    return ops.phase_consistency_cached(x.contiguous().float(), ops.phase_reference(ref.contiguous().float()), alpha)
+
+
+def svd_structure_preservation(x, k_ratio=0.5):
+    """Drop-in for svd_structure_preservation(x, k_ratio), 0409_method.ipynb#c0:L321-346."""
+    h, w = x.shape[-2:]
+    k = max(1, int(min(h, w) * k_ratio))
+    return ops.svd_lowrank(x.contiguous().float(), k)
+
+
+class GaussianMixtureSampler:
+    def __init__(self, model, num_timesteps=100, seed=0, noise_fn=None, coin_fn=None):
+        self.model = model
+        self.num_timesteps = num_timesteps
+        self.seed = seed
+        self.noise_fn = noise_fn
+        self.coin_fn = coin_fn
+
+    def sample(self, x_t, steps=100, use_phase_consistency=True, use_svd_guide=True, guidance_scale=1.0):
+        if not x_t.is_cuda:
+            raise RuntimeError("the B200 sampler runs on CUDA only (no CPU fallback)")
+        self.model.eval()
+        dev = x_t.device
+        x_t = x_t.contiguous().float().clone()
+        y = x_t.clone()
+        B = x_t.shape[0]
+        phasor = ops.phase_reference(y) if use_phase_consistency else None
+        with torch.no_grad():
+            for i in range(steps - 1, -1, -1):
+                t = torch.full((B,), float(i) / self.num_timesteps, dtype=torch.float32, device=dev)
+                pred = self.model(x_t, t, t)
+                prior, g = None, 0.0
+                if use_svd_guide and i > steps // 2:
+                    k_ratio = i / steps
+                    prior = svd_structure_preservation(x_t, k_ratio)
+                    g = k_ratio * 0.3
+                if i > 0:
+                    p_cons = max(0.2, min(0.8, i / steps))
+                    # the reference draws torch.rand(1) from the CPU generator (0409_method.ipynb#c1:L432)
+                    coin = self.coin_fn(i) if self.coin_fn is not None else torch.rand(1).item()
+                    z = self.noise_fn(i, x_t).contiguous() if self.noise_fn is not None else None
+                    x_n = ops.gmm_update(x_t, pred, y, prior, g, z=z, use_first=coin < p_cons,
+                                         noise_scale=0.1 * i / steps * guidance_scale, seed=self.seed, step=i)
+                    if use_phase_consistency and i % 5 == 0:
+                        x_n = ops.phase_consistency_cached(x_n, phasor, 0.6 + 0.3 * (1 - i / steps))
+                    x_t = x_n
+                else:
+                    x_t = ops.gmm_update(x_t, pred, y, prior, g, last_step=True)
+        return x_t

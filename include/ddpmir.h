@@ -1,0 +1,229 @@
+/*
+ * ddpmir.h -- C ABI of the B200-native (sm_100a) DDPM image-restoration hot path.
+ *
+ * The reference (Azure0413/DDPM_Image_Restoration) has no FFI / plugin layer: its only interface is a set of
+ * Python classes and functions whose device work goes through stock PyTorch ops.  Each entry point below
+ * therefore replaces one *op call site* of the reference's hot path (file:line given per function) and is what
+ * the Python classes in ddpm_image_restoration_b200/ bind through ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory unless its name ends in _host.
+ *   - the caller owns all buffers (outputs and workspaces); nothing here allocates, frees or synchronises.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous.
+ *   - return value: DDPMIR_OK (0) or a negative DDPMIR_ERR_* code; ddpmir_last_error() gives the text.
+ *   - activations inside the UNet are NHWC ("pixel-major"): [B, H, W, C] with C contiguous, element type
+ *     selected by `dtype` (DDPMIR_BF16 = production, DDPMIR_F32 = fp32 check mode).  Sampler-level images
+ *     are the reference's NCHW fp32 tensors in [-1, 1].
+ *   - weights are [N, K] row-major ("K-major") in the activation dtype; for 3x3 convolutions
+ *     K = 9 * Cin ordered (kh, kw, cin)  (pre-packed once on the host side from the checkpoint's OIHW fp32).
+ */
+#ifndef DDPMIR_H
+#define DDPMIR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDPMIR_OK 0
+#define DDPMIR_ERR_INVALID (-1)
+#define DDPMIR_ERR_CUDA (-2)
+#define DDPMIR_ERR_UNSUPPORTED (-3)
+
+#define DDPMIR_F32 0
+#define DDPMIR_BF16 1
+
+#define DDPMIR_ACT_NONE 0
+#define DDPMIR_ACT_RELU 1
+#define DDPMIR_ACT_LRELU02 2
+#define DDPMIR_ACT_SIGMOID 3
+#define DDPMIR_ACT_SILU 4
+#define DDPMIR_ACT_GELU 5
+#define DDPMIR_ACT_TANH 6
+
+/* kernel family selector for ops that have more than one implementation */
+#define DDPMIR_IMPL_AUTO 0
+#define DDPMIR_IMPL_SIMT 1   /* generic fp32-FMA kernels (the fp32 check mode; any shape) */
+#define DDPMIR_IMPL_TENSOR 2 /* tensor-core kernels (bf16 only; shape constraints apply) */
+
+typedef void* ddpmir_stream_t;
+
+int ddpmir_version(void);
+const char* ddpmir_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* Sampler-level kernels (NCHW fp32 images)                                                                */
+/* ------------------------------------------------------------------------------------------------------ */
+
+/* DDRM update, webp_inference.py:584-592,600 (avif_inference.py:441-449,457; svd.ipynb#c1:L367-375,383):
+ *     x' = x_theta - codec + y
+ *     out = eta_b*x' + (1-eta_b)*x_theta + eta*(z * (t[b]*sigma_scale))      (last_step: out = x')
+ * evaluated in the reference's own operation order with unfused fp32 ops, so it is bit-exact for an injected z.
+ * `codec` is either the reference's fp32 NCHW tensor (codec_u8_hwc = 0) or the decoder's raw uint8 HWC pixels
+ * (codec_u8_hwc = 1; converted as ToTensor + sub(0.5).mul(2.0) would, webp_inference.py:524-528).
+ * z == NULL: z is generated in-kernel, Philox4x32-10 keyed by (seed, step, noise_offset + flat NCHW element index)
+ * -- see ddpmir_philox_normal; noise_offset (a multiple of 4) lets a micro-batch address its slice of the
+ * whole-batch noise stream.  t is [B]. */
+int ddpmir_ddrm_update(const float* x_theta, const void* codec, int codec_u8_hwc, const float* y, const float* z,
+                       const float* t, float* out, int B, int C, int H, int W, float sigma_scale, float eta,
+                       float eta_b, int last_step, uint64_t seed, uint32_t step, uint64_t noise_offset,
+                       ddpmir_stream_t stream);
+
+/* GaussianMixtureSampler step, 0409_method.ipynb#c1:L411-447:
+ *     if svd_prior: pred = (1-g)*pred + g*(y - svd_prior)
+ *     last_step:    out = x_t + pred
+ *     else:         x0 = x_t + pred ; mean = use_first ? 0.9*x0 + 0.1*x_t : 1.1*x0 - 0.1*x_t ; out = mean + noise_scale*z
+ * z == NULL -> in-kernel Philox as above. */
+int ddpmir_gmm_update(const float* x_t, const float* pred, const float* y, const float* svd_prior, float g,
+                      const float* z, float* out, int64_t n, int use_first, float noise_scale, int last_step,
+                      uint64_t seed, uint32_t step, ddpmir_stream_t stream);
+
+/* Generic out = wa*a + wb*b (+ sigma*z): covers the classical DDPM posterior mean of
+ * experiments/code/ddpm.ipynb#c5:L63-76 (a = x_t, b = eps).  b may be NULL; z NULL + sigma != 0 -> Philox. */
+int ddpmir_lincomb(const float* a, float wa, const float* b, float wb, const float* z, float sigma, float* out,
+                   int64_t n, uint64_t seed, uint32_t step, ddpmir_stream_t stream);
+
+/* Standard normals from Philox4x32-10: element e takes word e%4 of Philox(counter=(e/4 mod 2^32, step, e/4 >> 32, 0),
+ * key=(seed_lo, seed_hi)); u = ((w >> 9) + 0.5) * 2^-23; Box-Muller on word pairs (0,1) and (2,3).
+ * Replaces torch.randn_like(x_t), webp_inference.py:589. */
+int ddpmir_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t step, ddpmir_stream_t stream);
+
+/* (x*127.5+127.5).clamp(0,255).to(uint8) -- truncating -- and NCHW -> HWC, webp_inference.py:509,514.
+ * out is [B, H, W, C] uint8 (device memory or mapped pinned host memory). */
+int ddpmir_quantize_u8_hwc(const float* x, uint8_t* out, int B, int C, int H, int W, ddpmir_stream_t stream);
+
+/* Inverse direction for the decoder's pixels: ToTensor() then .sub(0.5).mul(2.0), webp_inference.py:524-528.
+ * in [B, H, W, C] uint8 -> out [B, C, H, W] fp32. */
+int ddpmir_u8_hwc_to_nchw(const uint8_t* in, float* out, int B, int C, int H, int W, ddpmir_stream_t stream);
+
+/* phase_consistency(x, ref, alpha), webp_inference.py:531-550, per [H, W] plane (H, W powers of two <= 1024).
+ * ddpmir_phase_reference caches exp(i*angle(fft2(ref))) once per trajectory (ref = y is constant);
+ * ddpmir_phase_consistency then does fft2(x) -> |.|*phasor -> ifft2 -> alpha*x + (1-alpha)*real.
+ * phasor and ws are [planes, H, W] complex64 (2 floats per element). */
+int ddpmir_phase_reference(const float* ref, int planes, int H, int W, float* phasor, float* ws,
+                           ddpmir_stream_t stream);
+int ddpmir_phase_consistency(const float* x, const float* phasor, float alpha, int planes, int H, int W,
+                             float* out, float* ws, ddpmir_stream_t stream);
+
+/* svd_structure_preservation, 0409_method.ipynb#c0:L321-346: rank-k truncation of every [H, W] plane
+ * (one-sided Jacobi on the rows).  ws: planes * (H*W + 2*H) floats.  out may alias nothing. */
+int ddpmir_svd_lowrank(const float* x, int planes, int H, int W, int k, float* out, float* ws, int sweeps,
+                       ddpmir_stream_t stream);
+
+/* channel-weighted L1 of color_preservation_loss / color_loss on clamped [0,1] images,
+ * 0409_method.ipynb#c0:L66-76, conv_deep.ipynb#c0:L60-73.  out_scalar[0] = 0.25 L1_R + 0.5 L1_G + 0.25 L1_B.
+ * ws: 3 doubles. */
+int ddpmir_color_l1(const float* pred, const float* target, int B, int H, int W, float* out_scalar, double* ws,
+                    ddpmir_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* UNet kernels                                                                                            */
+/* ------------------------------------------------------------------------------------------------------ */
+
+/* TimeEmbedding.forward, webp_inference.py:145-151: sin/cos features of t -> Linear -> SiLU -> Linear.
+ * w0 [4*dim, dim], w1 [dim, 4*dim] fp32 (checkpoint layout). ws: B*5*dim floats. out [B, dim] fp32. */
+int ddpmir_time_embed(const float* t, int B, int dim, const float* w0, const float* b0, const float* w1,
+                      const float* b1, float* ws, float* out, ddpmir_stream_t stream);
+
+/* out[r, n] = act(bias[n] + sum_k in[r,k] * w[n,k]) for a few rows (time_proj webp_inference.py:308; the pooled
+ * multi-scale gates avif_inference.py:193-201).  All fp32. */
+int ddpmir_linear_rows(const float* in, int rows, int K, const float* w, const float* bias, int N, int act,
+                       float* out, ddpmir_stream_t stream);
+
+/* GroupNorm statistics, nn.GroupNorm webp_inference.py:281,290,363 (eps 1e-5, biased variance).
+ * x is NHWC (nchw = 0) or the NCHW fp32 network input (nchw = 1, dtype must be F32).
+ * mean_rstd: [B, G, 2] fp32.  ws: B*G*2 doubles. */
+int ddpmir_groupnorm_stats(const void* x, int dtype, int nchw, int B, int HW, int C, int G, float eps,
+                           float* mean_rstd, double* ws, ddpmir_stream_t stream);
+
+/* y = act((x - mean) * rstd * gamma[c] + beta[c]) on NHWC; act in {NONE, GELU, SILU} (webp_inference.py:304,
+ * 311-312, 363-364). */
+int ddpmir_groupnorm_apply(const void* x, int dtype, int B, int HW, int C, int G, const float* mean_rstd,
+                           const float* gamma, const float* beta, int act, void* out, ddpmir_stream_t stream);
+
+/* Convolution of the 3-channel NCHW fp32 network input (conv1 and the 1x1 shortcut of down1,
+ * webp_inference.py:282,301,337), optionally folding norm1 (mean_rstd/gamma/beta non-NULL):
+ * out[b,h,w,n] = bias[n] + row_bias[b,n] + sum w[n,c,kh,kw] * gn(x)[b,c,h+kh-p,w+kw-p]   (zero padding after GN).
+ * w is the checkpoint's OIHW fp32; ksize 1 or 3; out is NHWC `dtype`. */
+int ddpmir_conv_input(const float* x, int B, int Cin, int H, int W, const float* mean_rstd, const float* gamma,
+                      const float* beta, const float* w, const float* bias, const float* row_bias, int N,
+                      int ksize, int dtype, void* out, ddpmir_stream_t stream);
+
+/* Epilogue shared by ddpmir_conv3x3 and ddpmir_gemm; m = flat pixel index (b, h, w), n = output channel:
+ *     v = acc + bias[n] (+ row_bias[b, n])                      bias2 replaces bias on high-frequency pixels (freq_mode 2)
+ *     v = act(v)
+ *     freq_mode 1:  v = 0 unless (n < N/2) == is_low(h, w)      hidden layer of the stacked low/high gate MLP
+ *     freq_mode 2:  v *= is_low ? 1 : img_scale[b]              high_boost, webp_inference.py:263-264
+ *     otherwise  :  v *= img_scale[b]  (if given)
+ *     v *= mul[m, n] (if given);  v += res[m, n] (if given)
+ * is_low(h, w) restates the block loop of webp_inference.py:241-252 with block size `bs` and low size `low`. */
+typedef struct {
+    const float* bias;
+    const float* bias2;
+    const float* row_bias;
+    const float* img_scale;
+    const void* mul;
+    const void* res;
+    int act;
+    int freq_mode;
+    int bs;
+    int low;
+} ddpmir_epilogue_t;
+
+/* nn.Conv2d(Cin, N, 3, padding=1) on NHWC as an implicit GEMM (webp_inference.py:282,292,229; the AVIF edge
+ * convs avif_inference.py:213-215).  Cin % 16 == 0.  w: [N, 9*Cin] (kh,kw,cin). */
+int ddpmir_conv3x3(const void* x, int dtype, int B, int H, int W, int Cin, const void* w, int N,
+                   const ddpmir_epilogue_t* epi, void* out, int impl, ddpmir_stream_t stream);
+
+/* 1x1 convolutions / nn.Linear over pixels (shortcut :301, gate MLPs :215-225, MHA in/out projections :295):
+ * a is [B*H*W, K], w is [N, K].  K % 16 == 0. */
+int ddpmir_gemm(const void* a, int dtype, int B, int H, int W, int K, const void* w, int N,
+                const ddpmir_epilogue_t* epi, void* out, int impl, ddpmir_stream_t stream);
+
+/* Self-attention core of nn.MultiheadAttention(C, heads, batch_first=True) over L = H*W tokens
+ * (webp_inference.py:317-319): qkv is the in_proj output [B, L, 3C] (q | k | v, head h owns channels
+ * [h*hd, (h+1)*hd)); out [B, L, C] = softmax(q k^T / sqrt(hd)) v, never materialising the L x L scores. */
+int ddpmir_attention(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, int impl,
+                     ddpmir_stream_t stream);
+
+/* Blockwise per-channel transform  out = alpha*x + beta * (T_c X T_c^T)  with zero padding to a multiple of bs
+ * and crop back: DCTLayer.forward webp_inference.py:161-192 (per_channel = 0, T [bs,bs]) and
+ * AVIFAdaptiveTransform avif_inference.py:140-177 (per_channel = 1, T [C,bs,bs]).  bs in {4, 8}. T fp32. */
+int ddpmir_block_transform(const void* x, int dtype, int B, int H, int W, int C, const float* T, int bs,
+                           int per_channel, float alpha, float beta, void* out, ddpmir_stream_t stream);
+
+/* nn.MaxPool2d(2), webp_inference.py:342.  out [B, H/2, W/2, C]. */
+int ddpmir_maxpool2(const void* x, int dtype, int B, int H, int W, int C, void* out, ddpmir_stream_t stream);
+
+/* torch.cat([F.interpolate(lo, scale_factor=2, mode='bilinear', align_corners=False), skip], dim=1),
+ * webp_inference.py:389-393.  lo [B,H,W,C1], skip [B,2H,2W,C2], out [B,2H,2W,C1+C2]. */
+int ddpmir_upsample2_concat(const void* lo, const void* skip, int dtype, int B, int H, int W, int C1, int C2,
+                            void* out, ddpmir_stream_t stream);
+
+/* AdaptiveAvgPool2d(s) for s in {1,2,4,8}, avif_inference.py:195: out [85, B, C] fp32 (cell-major so that the
+ * rows of one scale are contiguous for ddpmir_linear_rows), cells ordered s=1 (1), s=2 (4, row-major), s=4 (16),
+ * s=8 (64).  Any H, W (PyTorch's adaptive window rule). */
+int ddpmir_avgpool_pyramid(const void* x, int dtype, int B, int H, int W, int C, float* out,
+                           ddpmir_stream_t stream);
+
+/* enhanced + residual of AVIFFreqAwareBlock.forward, avif_inference.py:226-256:
+ * out = h + xt * mean_s(bilinear_up(gates_s)) * color * edge, with gates [85,B,C] fp32 the sigmoid outputs of
+ * the pooled MLPs (F.interpolate(..., mode='bilinear', align_corners=False) restated in-kernel) and color/edge
+ * already multiplied by their boosts. */
+int ddpmir_avif_combine(const void* h, const void* xt, const float* gates, const void* color, const void* edge,
+                        int dtype, int B, int H, int W, int C, void* out, ddpmir_stream_t stream);
+
+/* out_conv tail, webp_inference.py:365-366: tanh(conv3x3(x) + bias), NHWC `dtype` in, NCHW fp32 out.
+ * w is the checkpoint's [3, Cin, 3, 3] fp32. */
+int ddpmir_out_conv_tanh(const void* x, int dtype, int B, int H, int W, int Cin, const float* w, const float* bias,
+                         int N, float* out, ddpmir_stream_t stream);
+
+/* dtype conversion helper for weight pre-packing (fp32 -> bf16, round-to-nearest-even). */
+int ddpmir_cast_f32_to_bf16(const float* in, void* out, int64_t n, ddpmir_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDPMIR_H */

@@ -1,0 +1,294 @@
+"""GPU parity tests, one per C-ABI kernel, against plain PyTorch fp32 on the CPU / the restated oracle.
+Tolerances: fp32 check mode <= 1e-5 relative L2 (north_star); bf16 mode <= 1e-2 (per-op it is ~3e-3);
+integer/byte work and the injected-noise update are bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restated as R
+from util import bf16_round, nchw, nhwc, pack1, pack3, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ddpm_image_restoration_b200 import ops as o
+    return o
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_philox_known_answer(ops):
+    n = 4096 + 3
+    z = ops.philox_normal((n,), seed=7, step=3).cpu().numpy()
+    ref = R.philox_normal(7, 3, n)
+    assert np.abs(z - ref).max() < 2e-5          # fp32 log/sincos vs float64
+    big = ops.philox_normal((1 << 22,), seed=(5 << 32) | 9, step=11).cpu()
+    assert abs(float(big.mean())) < 3e-3 and abs(float(big.std()) - 1) < 3e-3
+
+
+def test_ddrm_update_bit_exact(ops, golden):
+    d = golden("ops.npz")
+    xn, c, y, z, t = (torch.from_numpy(d[k]) for k in ("xn", "webp_q10", "x", "z", "t"))
+    for eta_b, key in ((1.0, "update_eta1"), (0.6, "update_eta06")):
+        out = ops.ddrm_update(xn.cuda(), c.cuda(), y.cuda(), t.cuda(), 0.2, 0.85, eta_b, z=z.cuda()).cpu()
+        assert torch.equal(out, torch.from_numpy(d[key]))
+    last = ops.ddrm_update(xn.cuda(), c.cuda(), y.cuda(), t.cuda(), 0.2, last_step=True).cpu()
+    assert torch.equal(last, xn - c + y)
+    # uint8 HWC decoder pixels path == fp32 path
+    u8 = ((c * 0.5 + 0.5) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    cf = u8.permute(0, 3, 1, 2).float().div(255).sub(0.5).mul(2.0)
+    a = ops.ddrm_update(xn.cuda(), u8.cuda(), y.cuda(), t.cuda(), 0.2, z=z.cuda()).cpu()
+    b = ops.ddrm_update(xn.cuda(), cf.cuda(), y.cuda(), t.cuda(), 0.2, z=z.cuda()).cpu()
+    assert torch.equal(a, b)
+    assert torch.equal(ops.u8_hwc_to_nchw(u8.cuda()).cpu(), cf)
+
+
+def test_ddrm_update_philox_and_offset(ops):
+    B, C, H, W = 4, 3, 16, 16
+    x, c, y = (torch.randn(B, C, H, W, generator=g(i)) for i in range(3))
+    t = torch.full((B,), 0.5)
+    z = torch.from_numpy(R.philox_normal(3, 9, x.numel()).astype(np.float32)).view_as(x)
+    ref = R.ddrm_update(x, c, y, z, t, 0.15)
+    out = ops.ddrm_update(x.cuda(), c.cuda(), y.cuda(), t.cuda(), 0.15, seed=3, step=9).cpu()
+    assert (out - ref).abs().max() < 1e-5
+    # micro-batch slices with noise_offset reproduce the full-batch stream
+    parts = [ops.ddrm_update(x[s:s + 2].cuda(), c[s:s + 2].cuda(), y[s:s + 2].cuda(), t[s:s + 2].cuda(), 0.15, seed=3,
+                             step=9, noise_offset=s * C * H * W).cpu() for s in (0, 2)]
+    assert torch.equal(torch.cat(parts), out)
+
+
+def test_gmm_update_and_lincomb(ops):
+    x, p, y, s, z = (torch.randn(2, 3, 32, 32, generator=g(10 + i)) for i in range(5))
+    gs = 0.21
+    pred = (1 - gs) * p + gs * (y - s)
+    x0 = x + pred
+    for first in (True, False):
+        mean = x0 * 0.9 + x * 0.1 if first else x0 * 1.1 - x * 0.1
+        ref = mean + 0.07 * z
+        out = ops.gmm_update(x.cuda(), p.cuda(), y.cuda(), s.cuda(), gs, z=z.cuda(), use_first=first, noise_scale=0.07).cpu()
+        assert (out - ref).abs().max() < 1e-6
+    out = ops.gmm_update(x.cuda(), p.cuda(), last_step=True).cpu()
+    assert torch.equal(out, x + p)
+    # classical DDPM posterior mean (ddpm.ipynb#c5)
+    tt = 57
+    betas, alphas, abar = R.ddpm_schedule(100)
+    ref = R.ddpm_posterior_mean(x, p, tt)
+    wa = float(1 / torch.sqrt(alphas[tt])); wb = float(-(1 - alphas[tt]) / torch.sqrt(1 - abar[tt]) / torch.sqrt(alphas[tt]))
+    out = ops.lincomb(x.cuda(), wa, p.cuda(), wb).cpu()
+    assert rel(out, ref) < 1e-6
+
+
+def test_quantize_u8(ops):
+    x = torch.randn(3, 3, 24, 40, generator=g(1)) * 0.8
+    x[0, 0, 0, :8] = torch.tensor([-1.0, 1.0, -1.2, 1.2, 0.0, 0.999, -0.999, 0.5])
+    out = ops.quantize_u8_hwc(x.cuda()).cpu()
+    assert torch.equal(out, R.quantize_u8(x).permute(0, 2, 3, 1))
+
+
+def test_color_l1(ops, golden):
+    d = golden("ops.npz")
+    xn, x = torch.from_numpy(d["xn"]) * 1.5, torch.from_numpy(d["x"])
+    out = float(ops.color_l1(xn.cuda(), x.cuda()))
+    assert abs(out - float(d["color_deep"])) < 1e-6
+    assert abs(out - float(R.color_l1(xn, x))) < 1e-6
+
+
+def test_time_embed_and_linear_rows(ops):
+    sd = {"time_embed.proj.0.weight": torch.randn(1024, 256, generator=g(1)) / 16, "time_embed.proj.0.bias": torch.randn(1024, generator=g(2)) * 0.1,
+          "time_embed.proj.2.weight": torch.randn(256, 1024, generator=g(3)) / 32, "time_embed.proj.2.bias": torch.randn(256, generator=g(4)) * 0.1}
+    t = torch.tensor([0.0, 0.37, 0.8, 0.9875])
+    ref = R.time_embedding(sd, t)
+    out = ops.time_embed(t.cuda(), *(sd[k].cuda() for k in sd)).cpu()
+    assert rel(out, ref) < 1e-5
+    x = torch.randn(5, 96, generator=g(5)); w = torch.randn(40, 96, generator=g(6)); b = torch.randn(40, generator=g(7))
+    out = ops.linear_rows(x.cuda(), w.cuda(), b.cuda(), ops.ACT_SIGMOID).cpu()
+    assert rel(out, torch.sigmoid(F.linear(x, w, b))) < 1e-6
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16), (1, 1024, 2, 2), (2, 128, 1, 1), (3, 256, 8, 24)])
+def test_groupnorm(ops, dtype, tol, shape):
+    B, C, H, W = shape
+    x = torch.randn(shape, generator=g(3)) * 2 + 0.7
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    gamma, beta = torch.randn(C, generator=g(4)), torch.randn(C, generator=g(5))
+    xd = nhwc(x, dtype)
+    st = ops.groupnorm_stats(xd, 8)
+    for act, fn in ((ops.ACT_NONE, lambda v: v), (ops.ACT_GELU, F.gelu), (ops.ACT_SILU, F.silu)):
+        ref = fn(F.group_norm(x, 8, gamma, beta, 1e-5))
+        out = nchw(ops.groupnorm_apply(xd, st, gamma.cuda(), beta.cuda(), act))
+        assert rel(out, ref) < tol
+
+
+def test_groupnorm_nchw_and_conv_input(ops):
+    x = torch.randn(2, 3, 32, 32, generator=g(1)) * 0.6 + 0.1
+    gamma, beta = torch.randn(3, generator=g(2)), torch.randn(3, generator=g(3))
+    w, b = torch.randn(64, 3, 3, 3, generator=g(4)) / 5, torch.randn(64, generator=g(5))
+    tb = torch.randn(2, 64, generator=g(6))
+    st = ops.groupnorm_stats(x.cuda(), 3, nchw=True)
+    ref = F.conv2d(F.group_norm(x, 3, gamma, beta, 1e-5), w, b, padding=1) + tb[:, :, None, None]
+    out = nchw(ops.conv_input(x.cuda(), w.cuda(), b.cuda(), torch.float32, st, gamma.cuda(), beta.cuda(), row_bias=tb.cuda()))
+    assert rel(out, ref) < 1e-5
+    w1 = torch.randn(64, 3, 1, 1, generator=g(7))
+    out = nchw(ops.conv_input(x.cuda(), w1.cuda(), b.cuda(), torch.bfloat16))
+    assert rel(out, F.conv2d(x, w1, b)) < 5e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("shape", [(2, 64, 128, 16, 16), (1, 128, 32, 8, 8), (3, 32, 64, 5, 7), (1, 1024, 512, 2, 2), (2, 16, 192, 1, 1)])
+def test_conv3x3_generic(ops, dtype, tol, shape):
+    B, Ci, Co, H, W = shape
+    x = torch.randn(B, Ci, H, W, generator=g(1))
+    w = torch.randn(Co, Ci, 3, 3, generator=g(2)) / math.sqrt(9 * Ci)
+    b = torch.randn(Co, generator=g(3))
+    tb = torch.randn(B, Co, generator=g(4))
+    res = torch.randn(B, Co, H, W, generator=g(5))
+    if dtype == torch.bfloat16:
+        x, w, res = bf16_round(x), bf16_round(w), bf16_round(res)
+    ref = F.conv2d(x, w, b, padding=1) + tb[:, :, None, None] + res
+    out = nchw(ops.conv3x3(nhwc(x, dtype), pack3(w, dtype), Co, ops.IMPL_SIMT, bias=b.cuda(), row_bias=tb.cuda(), res=nhwc(res, dtype)))
+    assert rel(out, ref) < tol
+    scale = torch.rand(B, generator=g(6)) + 0.5
+    ref = torch.sigmoid(F.conv2d(x, w, b, padding=1)) * scale.view(-1, 1, 1, 1)
+    out = nchw(ops.conv3x3(nhwc(x, dtype), pack3(w, dtype), Co, ops.IMPL_SIMT, bias=b.cuda(), act=ops.ACT_SIGMOID, img_scale=scale.cuda()))
+    assert rel(out, ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("fam,hw", [("webp", (16, 16)), ("jpeg", (16, 24)), ("webp", (2, 2)), ("jpeg", (4, 4)), ("webp", (1, 1))])
+def test_dct_freq_block_composite(ops, dtype, tol, fam, hw):
+    """block_transform + stacked gate GEMMs (freq_mode 1/2) + conv_out == WebP/JPEGFreqAwareBlock.forward."""
+    C, B = 64, 2
+    H, W = hw
+    f = R.FAMILY[fam]
+    gen = g(11)
+    rnd = lambda *s: torch.randn(*s, generator=gen)
+    sd = {"p.dct.dct_matrix": R.dct_matrix(f["bs"])}
+    for gname in ("low_freq_attn", "high_freq_attn"):
+        sd[f"p.{gname}.0.weight"] = rnd(C // 2, C, 1, 1) / 8; sd[f"p.{gname}.0.bias"] = rnd(C // 2) * 0.3
+        sd[f"p.{gname}.2.weight"] = rnd(C, C // 2, 1, 1) / 5; sd[f"p.{gname}.2.bias"] = rnd(C) * 0.3
+    sd["p.conv_out.weight"] = rnd(C, C, 3, 3) / 24; sd["p.conv_out.bias"] = rnd(C) * 0.1
+    x = rnd(B, C, H, W)
+    level = torch.tensor([0.2, 0.95])
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+        sd = {k: (bf16_round(v) if k.endswith("weight") else v) for k, v in sd.items()}
+    ref = R.dct_freq_block(sd, "p", x, level, f)
+    xd = nhwc(x, dtype)
+    d = ops.block_transform(xd, sd["p.dct.dct_matrix"].cuda(), 0.0, 1.0)
+    assert rel(nchw(d), R.block_transform(x, sd["p.dct.dct_matrix"])) < (1e-6 if dtype == torch.float32 else 4e-3)
+    w1 = torch.cat([sd["p.low_freq_attn.0.weight"], sd["p.high_freq_attn.0.weight"]], 0).reshape(C, C)
+    b1 = torch.cat([sd["p.low_freq_attn.0.bias"], sd["p.high_freq_attn.0.bias"]], 0)
+    w2 = torch.cat([sd["p.low_freq_attn.2.weight"].reshape(C, C // 2), sd["p.high_freq_attn.2.weight"].reshape(C, C // 2)], 1)
+    boost = torch.clamp(1.0 - level, f["clamp"][0], f["clamp"][1])
+    g1 = ops.gemm(d, pack1(w1, dtype), C, ops.IMPL_SIMT, bias=b1.cuda(), act=ops.ACT_LRELU02, freq_mode=1, bs=f["bs"], low=f["low"])
+    e = ops.gemm(g1, pack1(w2, dtype), C, ops.IMPL_SIMT, bias=sd["p.low_freq_attn.2.bias"].cuda(), bias2=sd["p.high_freq_attn.2.bias"].cuda(),
+                 act=ops.ACT_SIGMOID, freq_mode=2, bs=f["bs"], low=f["low"], img_scale=boost.cuda(), mul=d, res=xd)
+    out = nchw(ops.conv3x3(e, pack3(sd["p.conv_out.weight"], dtype), C, ops.IMPL_SIMT, bias=sd["p.conv_out.bias"].cuda()))
+    assert rel(out, ref) < tol
+
+
+@pytest.mark.parametrize("per_channel,bs,hw", [(0, 4, (10, 7)), (0, 8, (16, 16)), (1, 8, (8, 24)), (1, 8, (3, 5)), (0, 8, (1, 1))])
+def test_block_transform(ops, per_channel, bs, hw):
+    C = 96
+    x = torch.randn(2, C, *hw, generator=g(1))
+    T = torch.randn(C, bs, bs, generator=g(2)) if per_channel else R.dct_matrix(bs)
+    ref = 0.3 * x + 1.7 * R.block_transform(x, T)
+    out = nchw(ops.block_transform(nhwc(x), T.cuda(), 0.3, 1.7))
+    assert rel(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pool_upsample_concat(ops, dtype):
+    x = torch.randn(2, 64, 12, 20, generator=g(1))
+    skip = torch.randn(2, 32, 24, 40, generator=g(2))
+    if dtype == torch.bfloat16:
+        x, skip = bf16_round(x), bf16_round(skip)
+    assert torch.equal(nchw(ops.maxpool2(nhwc(x, dtype))), F.max_pool2d(x, 2))
+    ref = torch.cat([F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), skip], 1)
+    out = nchw(ops.upsample2_concat(nhwc(x, dtype), nhwc(skip, dtype)))
+    assert rel(out, ref) < (1e-6 if dtype == torch.float32 else 4e-3)
+    one = torch.randn(1, 16, 1, 1, generator=g(3)); sk = torch.randn(1, 8, 2, 2, generator=g(4))
+    ref = torch.cat([F.interpolate(one, scale_factor=2, mode="bilinear", align_corners=False), sk], 1)
+    assert rel(nchw(ops.upsample2_concat(nhwc(one), nhwc(sk))), ref) < 1e-6
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (8, 8), (4, 4), (2, 2), (1, 1), (24, 40)])
+def test_avif_pyramid_and_combine(ops, hw):
+    B, C = 2, 64
+    H, W = hw
+    gen = g(5)
+    h = torch.randn(B, C, H, W, generator=gen)
+    xt, color, edge = (torch.randn(B, C, H, W, generator=gen) for _ in range(3))
+    pooled = ops.avgpool_pyramid(nhwc(h)).cpu()      # [85, B, C]
+    off = 0
+    gates = torch.rand(85, B, C, generator=gen)
+    acc = 0
+    for s in (1, 2, 4, 8):
+        ref = F.adaptive_avg_pool2d(h, s)            # [B, C, s, s]
+        got = pooled[off:off + s * s].view(s, s, B, C).permute(2, 3, 0, 1)
+        assert rel(got, ref) < 1e-6
+        gmap = gates[off:off + s * s].view(s, s, B, C).permute(2, 3, 0, 1).contiguous()
+        if gmap.shape != h.shape:
+            gmap = F.interpolate(gmap, size=(H, W), mode="bilinear", align_corners=False)
+        acc = acc + gmap
+        off += s * s
+    ref = h + xt * (acc / 4) * color * edge
+    out = nchw(ops.avif_combine(nhwc(h), nhwc(xt), gates.cuda(), nhwc(color), nhwc(edge)))
+    assert rel(out, ref) < 1e-6
+
+
+def test_out_conv_tanh(ops):
+    x = torch.randn(2, 64, 16, 24, generator=g(1))
+    w, b = torch.randn(3, 64, 3, 3, generator=g(2)) / 24, torch.randn(3, generator=g(3)) * 0.1
+    ref = torch.tanh(F.conv2d(x, w, b, padding=1))
+    assert rel(ops.out_conv_tanh(nhwc(x), w.cuda(), b.cuda()).cpu(), ref) < 1e-5
+    assert rel(ops.out_conv_tanh(nhwc(bf16_round(x), torch.bfloat16), w.cuda(), b.cuda()).cpu(), torch.tanh(F.conv2d(bf16_round(x), w, b, padding=1))) < 1e-5
+
+
+def _attn_ref(qkv, heads):
+    B, L, C3 = qkv.shape
+    C = C3 // 3
+    q, k, v = qkv.view(B, L, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    return F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, C)
+
+
+@pytest.mark.parametrize("hd,heads,L", [(8, 8, 100), (16, 4, 64), (16, 4, 1), (32, 4, 257), (64, 4, 16), (128, 4, 4), (256, 4, 64)])
+def test_attention_simt_fp32(ops, hd, heads, L):
+    C = hd * heads
+    qkv = torch.randn(2, L, 3 * C, generator=g(hd + L))
+    out = ops.attention(qkv.cuda(), heads, ops.IMPL_SIMT).cpu()
+    assert rel(out, _attn_ref(qkv, heads)) < 1e-5
+
+
+@pytest.mark.parametrize("expmode", [0, 1])
+@pytest.mark.parametrize("hd,heads,L", [(8, 8, 1024), (16, 4, 1024), (16, 4, 64), (32, 4, 256), (64, 4, 256), (128, 4, 128), (16, 4, 4096)])
+def test_attention_tensor_core_bf16(ops, expmode, hd, heads, L):
+    from ddpm_image_restoration_b200 import _lib
+    C = hd * heads
+    qkv = bf16_round(torch.randn(2, L, 3 * C, generator=g(hd + L)) * 1.5)
+    _lib.lib().ddpmir_attention_set_expmode(expmode)
+    try:
+        out = ops.attention(qkv.to(torch.bfloat16).cuda(), heads, ops.IMPL_TENSOR).float().cpu()
+    finally:
+        _lib.lib().ddpmir_attention_set_expmode(0)
+    tol = 6e-3 if expmode == 0 else 1.5e-2
+    assert rel(out, _attn_ref(qkv, heads)) < tol
+    # and the bf16 SIMT kernel agrees too
+    out2 = ops.attention(qkv.to(torch.bfloat16).cuda(), heads, ops.IMPL_SIMT).float().cpu()
+    assert rel(out2, _attn_ref(qkv, heads)) < 4e-3
+
+
+def test_cpu_tensor_raises(ops):
+    from ddpm_image_restoration_b200._lib import DdpmirError
+    with pytest.raises(DdpmirError):
+        ops.maxpool2(torch.zeros(1, 2, 2, 8))

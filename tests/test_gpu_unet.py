@@ -1,0 +1,74 @@
+"""UNet forward parity on the GPU: against the reference's own outputs (tests/golden/unet_*.npz, minted by
+oracle/make_golden.py from the unmodified reference) and against the restated oracle at other sizes.
+north_star tolerances: relative L2 <= 1e-5 in the fp32 check mode, <= 1e-2 in bf16."""
+import pytest
+import torch
+
+from oracle import restated as R
+from oracle import weights as W
+from util import rel
+
+pytestmark = pytest.mark.gpu
+
+CLS = {"webp": "WebPDiffusionModel", "jpeg": "JPEGDiffusionModel", "avif": "AVIFDiffusionModel"}
+_models = {}
+
+
+def model(fam):
+    import ddpm_image_restoration_b200 as P
+    if fam not in _models:
+        m = getattr(P, CLS[fam])()
+        m.load_state_dict(W.make_state_dict(fam, 0))
+        _models[fam] = m.cuda().eval()
+    return _models[fam]
+
+
+@pytest.mark.parametrize("fam,hw", [("webp", 32), ("jpeg", 32), ("avif", 32), ("webp", 64), ("avif", 64)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_unet_vs_reference_golden(golden, fam, hw, precision, tol):
+    d = golden(f"unet_{fam}_{hw}.npz")
+    m = model(fam).set_precision(precision)
+    x, t, lvl = (torch.from_numpy(d[k]).cuda() for k in ("x", "t", "level"))
+    out = m(x, t, lvl).cpu()
+    assert rel(out, torch.from_numpy(d["out"])) < tol
+    out = m(x, t).cpu()      # compression_level=None -> t  (webp_inference.py:373-374)
+    assert rel(out, torch.from_numpy(d["out_nolevel"])) < tol
+
+
+@pytest.mark.parametrize("fam", ["webp", "avif"])
+def test_unet_block_taps_fp32(golden, fam):
+    """Per-block outputs of the check mode against the reference's forward hooks."""
+    d = golden(f"unet_{fam}_32.npz")
+    m = model(fam).set_precision("fp32")
+    x, t, lvl = (torch.from_numpy(d[k]).cuda() for k in ("x", "t", "level"))
+    taps = {}
+    with torch.no_grad():
+        m._forward(x, t, lvl, taps)
+    for name, key in (("d1", "tap_down1"), ("d3", "tap_down3"), ("bn", "tap_bottleneck"), ("u5", "tap_up5")):
+        got = taps[name].float().permute(0, 3, 1, 2)[:, ::4, ::2, ::2].cpu()
+        assert rel(got, torch.from_numpy(d[key])) < 1e-5, name
+
+
+@pytest.mark.parametrize("fam", ["webp", "avif"])
+def test_unet_128_vs_oracle(fam):
+    """A size the goldens do not hold, checked against the restated oracle computed live (a few seconds)."""
+    sd = W.make_state_dict(fam, 0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 3, 128, 128, generator=g) * 0.5
+    t = torch.tensor([0.6125])
+    ref = R.unet_forward(sd, x, t, None, fam)
+    for precision, tol in (("fp32", 1e-5), ("bf16", 1e-2)):
+        out = model(fam).set_precision(precision)(x.cuda(), t.cuda()).cpu()
+        assert rel(out, ref) < tol, precision
+
+
+def test_training_mode_and_cpu_raise():
+    m = model("webp")
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 32, 32), torch.zeros(1))
+    m.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            m(torch.zeros(1, 3, 32, 32).cuda(), torch.zeros(1).cuda())
+    finally:
+        m.eval()
