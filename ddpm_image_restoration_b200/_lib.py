@@ -18,8 +18,9 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
 class Epilogue(ctypes.Structure):
     """Mirror of ddpmir_epilogue_t."""
     _fields_ = [("bias", c_void_p), ("bias2", c_void_p), ("row_bias", c_void_p), ("img_scale", c_void_p),
-                ("mul", c_void_p), ("res", c_void_p), ("act", c_int), ("freq_mode", c_int), ("bs", c_int),
-                ("low", c_int)]
+                ("mul", c_void_p), ("res", c_void_p), ("out2", c_void_p), ("act", c_int), ("freq_mode", c_int),
+                ("bs", c_int), ("low", c_int), ("out_dtype", c_int), ("out2_dtype", c_int), ("mul_dtype", c_int),
+                ("res_dtype", c_int)]
 
 
 _P = c_void_p
@@ -27,7 +28,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "ddpmir_version": (c_int, []),
     "ddpmir_last_error": (c_char_p, []),
-    "ddpmir_ddrm_update": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+    "ddpmir_ddrm_update": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                    c_int, c_uint64, c_uint32, c_uint64, _P]),
     "ddpmir_gmm_update": (c_int, [_P, _P, _P, _P, c_float, _P, _P, c_int64, c_int, c_float, c_int, c_uint64, c_uint32, _P]),
     "ddpmir_lincomb": (c_int, [_P, c_float, _P, c_float, _P, c_float, _P, c_int64, c_uint64, c_uint32, _P]),
@@ -41,16 +42,16 @@ _SIGNATURES = {
     "ddpmir_time_embed": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "ddpmir_linear_rows": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "ddpmir_groupnorm_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
-    "ddpmir_groupnorm_apply": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
+    "ddpmir_groupnorm_apply": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P]),
     "ddpmir_conv_input": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "ddpmir_conv3x3": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
     "ddpmir_gemm": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
     "ddpmir_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
-    "ddpmir_block_transform": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ddpmir_block_transform": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "ddpmir_maxpool2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_upsample2_concat": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_avgpool_pyramid": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
-    "ddpmir_avif_combine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_avif_combine": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_out_conv_tanh": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
     "ddpmir_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
 }

@@ -107,7 +107,7 @@ def _compress(x, quality, codec):
     # host tensors: the whole operator is host work
     u8 = (x.float() * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy()
     dec = roundtrip_u8(codec, quality, u8)
-    return torch.from_numpy(dec).permute(0, 3, 1, 2).float().div(255.0).sub(0.5).mul(2.0)
+    return torch.from_numpy(dec).permute(0, 3, 1, 2).contiguous().float().div(255.0).sub(0.5).mul(2.0)
 
 
 def webp_compress(x, quality):

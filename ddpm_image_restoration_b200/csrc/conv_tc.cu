@@ -1,7 +1,295 @@
-// tcgen05 / TMA implicit-GEMM convolution (placeholder until the kernel lands: reports "unsupported" so the
-// router falls back to the generic kernel).
+// tcgen05 / TMEM / TMA implicit-GEMM for the UNet's 3x3 convolutions (9 taps) and 1x1 convolutions / linears
+// (1 tap) on NHWC bf16 activations, sm_100a only.
+//
+//   out[m, n] = epilogue( sum_{tap, c} X[pixel(m) + off(tap), c] * Wt[n, tap*Cin + c] )
+//
+// * A operand: no im2col buffer.  The activation tensor is described to TMA as a 4-D tensor (C, W, H, B); the 128
+//   output pixels of a CTA tile form a box (64 ch, bw, bh, bb) with bw*bh*bb = 128, and each filter tap is the SAME box
+//   shifted by (kw-1, kh-1).  Out-of-image coordinates (the zero padding of Conv2d(padding=1)) are zero-filled by TMA,
+//   also at image boundaries inside a multi-image box because W/H/B are separate tensor dimensions.
+// * The box lands in shared memory as 128 rows x 128 B with the hardware 128B swizzle = a K-major SWIZZLE_128B UMMA
+//   operand tile; the weights [N, 9*Cin] (K-major) are loaded the same way.  4-stage mbarrier ring.
+// * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16, bf16 x bf16 -> fp32) into TMEM; tcgen05.commit
+//   releases the shared-memory stage / signals the epilogue.
+// * Epilogue warps read the accumulator with tcgen05.ld (one TMEM lane = one output pixel per thread), apply the
+//   fused epilogue (bias, time-embedding row bias, activation, frequency gates, residual; epilogue.cuh) and store the
+//   fp32 stream and/or bf16 operand copy.
+#include <cuda.h>
 #include "epilogue.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;      // 64 bf16 = 128 B = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    // bounded spin: a protocol bug must trap (launch failure), never hang the GPU
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 (8 rows x 128 B = 1024)
+//   [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TcParams {
+    long long M;
+    int H, W, Cin, N;
+    int bw, bh;            // pixel box = (bw, bh, 128/(bw*bh)) over (W, H, B)
+    int taps;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void* __restrict__ out,
+                EpiDev ep, TcParams p) {
+    constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // SWIZZLE_128B tiles must start on 1024-byte boundaries of the shared address space
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sa = smem;                                   // STAGES x 16 KB (1024-B aligned tiles)
+    unsigned char* sb = smem + STAGES * A_STAGE_BYTES;          // STAGES x B tiles
+    uint64_t* full = reinterpret_cast<uint64_t*>(sb + STAGES * B_STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * BLOCK_M;
+    const int n0 = blockIdx.y * BLOCK_N;
+    const int kc = p.Cin / BLOCK_K;          // k-blocks per tap
+    const int num_kb = p.taps * kc;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----
+            const int hw = p.H * p.W;
+            const int b0 = (int)(m0 / hw);
+            const int rem = (int)(m0 - (long long)b0 * hw);
+            const int h0 = rem / p.W, w0 = rem - h0 * p.W;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = kb / kc, c0 = (kb - tap * kc) * BLOCK_K;
+                const int dh = p.taps == 9 ? tap / 3 - 1 : 0, dw = p.taps == 9 ? tap % 3 - 1 : 0;
+                mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
+                tma_load_4d(sa + s * A_STAGE_BYTES, &tmap_a, &full[s], c0, w0 + dw, h0 + dh, b0);
+                tma_load_2d(sb + s * B_STAGE_BYTES, &tmap_b, &full[s], tap * p.Cin + c0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+            // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sa + s * A_STAGE_BYTES), b_addr = smem_u32(sb + s * B_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                    const uint64_t da = make_desc_sw128(a_addr + k * 32), db = make_desc_sw128(b_addr + k * 32);
+                    umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);          // stage reusable once these MMAs have read it
+            }
+            umma_commit(acc_full);               // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 ----
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int lane_base = 32 * (warp & 3);
+        const long long m = m0 + lane_base + lane;
+        const bool m_ok = m < p.M;
+        EpiRow row;
+        if (m_ok) row = epi_row(ep, m);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+            if (m_ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < p.N) epi_store(ep, out, m, n, epi_apply(ep, row, v[j], m, n));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev& ep, const TcParams& p, cudaStream_t st) {
+    constexpr int smem = STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { ddpmir_set_error("igemm_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BLOCK_N));
+    igemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, smem, st>>>(ta, tb, out, ep, p);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+}  // namespace
+
 int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const void* w, int N,
                     const ddpmir_epilogue_t* epi, void* out, cudaStream_t st) {
-    return DDPMIR_ERR_UNSUPPORTED;
+    // shape constraints of this kernel; anything else goes to the generic path
+    if (Cin % BLOCK_K != 0 || N % 8 != 0) return DDPMIR_ERR_UNSUPPORTED;
+    if (!pow2(H) || !pow2(W)) return DDPMIR_ERR_UNSUPPORTED;
+    if (((uintptr_t)x & 15) || ((uintptr_t)w & 15)) return DDPMIR_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { ddpmir_set_error("igemm_tc: cuTensorMapEncodeTiled not available"); return DDPMIR_ERR_CUDA; }
+
+    TcParams p;
+    p.M = (long long)B * H * W; p.H = H; p.W = W; p.Cin = Cin; p.N = N; p.taps = taps;
+    p.bw = W < BLOCK_M ? W : BLOCK_M;
+    p.bh = (BLOCK_M / p.bw) < H ? (BLOCK_M / p.bw) : H;
+    const int bb = BLOCK_M / (p.bw * p.bh);
+
+    CUtensorMap ta, tb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)bb};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ddpmir_set_error("igemm_tc: activation tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
+    }
+    const int block_n = (N % 128 == 0) ? 128 : 64;
+    {
+        const cuuint64_t K = (cuuint64_t)taps * Cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)N};
+        cuuint64_t strides[1] = {K * 2};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ddpmir_set_error("igemm_tc: weight tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
+    }
+    EpiDev ep = make_epi(epi, H, W, N, DDPMIR_BF16);
+    return block_n == 128 ? launch<128>(ta, tb, out, ep, p, st) : launch<64>(ta, tb, out, ep, p, st);
 }

@@ -9,15 +9,30 @@ struct EpiDev {
     const float* img_scale;
     const void* mul;
     const void* res;
+    void* out2;
     int act;
     int freq_mode;
     int bs;
     int low;
+    int out_dtype, out2_dtype, mul_dtype, res_dtype;
     int H, W, N;
 };
 
-static inline EpiDev make_epi(const ddpmir_epilogue_t* e, int H, int W, int N) {
+__device__ __forceinline__ float ld_any(const void* p, int dtype, long long i) {
+    return dtype == DDPMIR_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const bf16*>(p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, long long i, float v) {
+    if (dtype == DDPMIR_F32) reinterpret_cast<float*>(p)[i] = v;
+    else reinterpret_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+static inline EpiDev make_epi(const ddpmir_epilogue_t* e, int H, int W, int N, int operand_dtype) {
     EpiDev d;
+    d.out2 = e ? e->out2 : nullptr;
+    d.out_dtype = e ? e->out_dtype : operand_dtype;
+    d.out2_dtype = e ? e->out2_dtype : operand_dtype;
+    d.mul_dtype = e ? e->mul_dtype : operand_dtype;
+    d.res_dtype = e ? e->res_dtype : operand_dtype;
     d.bias = e ? e->bias : nullptr;
     d.bias2 = e ? e->bias2 : nullptr;
     d.row_bias = e ? e->row_bias : nullptr;
@@ -38,6 +53,9 @@ static inline int check_epi(const ddpmir_epilogue_t* e, int N) {
     if (e->freq_mode && (e->bs <= 0 || e->low <= 0)) { ddpmir_set_error("epilogue: freq_mode needs bs/low"); return DDPMIR_ERR_INVALID; }
     if (e->freq_mode == 1 && (N & 1)) { ddpmir_set_error("epilogue: freq_mode 1 needs even N"); return DDPMIR_ERR_INVALID; }
     if (e->freq_mode == 2 && (!e->bias2 || !e->bias)) { ddpmir_set_error("epilogue: freq_mode 2 needs bias and bias2"); return DDPMIR_ERR_INVALID; }
+    const int dts[4] = {e->out_dtype, e->out2_dtype, e->mul_dtype, e->res_dtype};
+    for (int i = 0; i < 4; ++i)
+        if (dts[i] != DDPMIR_F32 && dts[i] != DDPMIR_BF16) { ddpmir_set_error("epilogue: bad dtype field %d", dts[i]); return DDPMIR_ERR_INVALID; }
     return DDPMIR_OK;
 }
 
@@ -63,7 +81,6 @@ __device__ __forceinline__ EpiRow epi_row(const EpiDev& p, long long m) {
     return r;
 }
 
-template <typename T>
 __device__ __forceinline__ float epi_apply(const EpiDev& p, const EpiRow& r, float acc, long long m, int n) {
     float v = acc;
     if (p.freq_mode == 2 && !r.low) v += p.bias2[n];
@@ -74,7 +91,12 @@ __device__ __forceinline__ float epi_apply(const EpiDev& p, const EpiRow& r, flo
         if ((n < (p.N >> 1)) != r.low) v = 0.f;
     }
     v *= r.scale;
-    if (p.mul) v *= to_f(reinterpret_cast<const T*>(p.mul)[m * p.N + n]);
-    if (p.res) v += to_f(reinterpret_cast<const T*>(p.res)[m * p.N + n]);
+    if (p.mul) v *= ld_any(p.mul, p.mul_dtype, m * p.N + n);
+    if (p.res) v += ld_any(p.res, p.res_dtype, m * p.N + n);
     return v;
+}
+
+__device__ __forceinline__ void epi_store(const EpiDev& p, void* out, long long m, int n, float v) {
+    st_any(out, p.out_dtype, m * p.N + n, v);
+    if (p.out2) st_any(p.out2, p.out2_dtype, m * p.N + n, v);
 }

@@ -25,7 +25,7 @@ template <> struct Ld4<bf16> {
 
 template <typename T, int TAPS>
 __global__ void __launch_bounds__(256)
-igemm_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ out, EpiDev ep, long long M,
+igemm_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, void* __restrict__ out, EpiDev ep, long long M,
                   int H, int W, int Cin, int N) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -89,7 +89,7 @@ igemm_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < N) out[m * N + n] = from_f<T>(epi_apply<T>(ep, row, acc[i][j], m, n));
+            if (n < N) epi_store(ep, out, m, n, epi_apply(ep, row, acc[i][j], m, n));
         }
     }
 }
@@ -98,12 +98,12 @@ template <int TAPS>
 int launch(const void* x, int dtype, int B, int H, int W, int Cin, const void* w, int N, const ddpmir_epilogue_t* epi,
            void* out, cudaStream_t st) {
     const long long M = (long long)B * H * W;
-    EpiDev ep = make_epi(epi, H, W, N);
+    EpiDev ep = make_epi(epi, H, W, N, dtype);
     dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
     if (dtype == DDPMIR_F32)
-        igemm_simt_kernel<float, TAPS><<<grid, 256, 0, st>>>((const float*)x, (const float*)w, (float*)out, ep, M, H, W, Cin, N);
+        igemm_simt_kernel<float, TAPS><<<grid, 256, 0, st>>>((const float*)x, (const float*)w, out, ep, M, H, W, Cin, N);
     else
-        igemm_simt_kernel<bf16, TAPS><<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)out, ep, M, H, W, Cin, N);
+        igemm_simt_kernel<bf16, TAPS><<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)w, out, ep, M, H, W, Cin, N);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

@@ -74,10 +74,10 @@ __global__ void gn_finalize_kernel(const double* __restrict__ ws, int count, dou
 }
 
 // ---- apply ----------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long total_vec, int HW, int C, int G,
-                const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+gn_apply_kernel(const T* __restrict__ x, TO* __restrict__ out, TO* __restrict__ raw_copy, long long total_vec, int HW,
+                int C, int G, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int act) {
     const int cv = C >> 3;
     const int cpg = C / G;
@@ -91,13 +91,19 @@ gn_apply_kernel(const T* __restrict__ x, T* __restrict__ out, long long total_ve
         const float mean = mean_rstd[((long long)b * G + g) * 2], rstd = mean_rstd[((long long)b * G + g) * 2 + 1];
         Vec8<T> a;
         a.load(x + i * 8);
+        Vec8<TO> o;
+        if (raw_copy) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = a.v[k];
+            o.store(raw_copy + i * 8);
+        }
         const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a.v[k] = act_apply(act, fmaf((a.v[k] - mean) * rstd, gg[k], bb[k]));
-        a.store(out + i * 8);
+        for (int k = 0; k < 8; ++k) o.v[k] = act_apply(act, fmaf((a.v[k] - mean) * rstd, gg[k], bb[k]));
+        o.store(out + i * 8);
     }
 }
 
@@ -229,18 +235,18 @@ extern "C" int ddpmir_groupnorm_stats(const void* x, int dtype, int nchw, int B,
 }
 
 extern "C" int ddpmir_groupnorm_apply(const void* x, int dtype, int B, int HW, int C, int G, const float* mean_rstd,
-                                      const float* gamma, const float* beta, int act, void* out,
-                                      ddpmir_stream_t stream) {
+                                      const float* gamma, const float* beta, int act, void* out, int out_dtype,
+                                      void* raw_copy, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(x && out && mean_rstd && gamma && beta, "groupnorm_apply: null pointer");
     DDPMIR_CHECK_ARG(C % 8 == 0 && C % G == 0 && (C / G) % 8 == 0, "groupnorm_apply: unsupported C=%d G=%d", C, G);
     const long long total = (long long)B * HW * (C / 8);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DDPMIR_F32)
-        gn_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, total, HW, C, G, mean_rstd, gamma, beta, act);
-    else
-        gn_apply_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, total, HW, C, G, mean_rstd, gamma, beta, act);
+#define GO(TI, TO) gn_apply_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x, (TO*)out, (TO*)raw_copy, total, HW, C, G, mean_rstd, gamma, beta, act)
+    if (dtype == DDPMIR_F32) { if (out_dtype == DDPMIR_F32) GO(float, float); else GO(float, bf16); }
+    else { if (out_dtype == DDPMIR_F32) GO(bf16, float); else GO(bf16, bf16); }
+#undef GO
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

@@ -7,9 +7,9 @@ namespace {
 // ---- blockwise transform  out = alpha*x + beta*(T X T^T) -------------------------------------------------
 // CTA = 64 channels (threadIdx.x) x 4 spatial blocks (threadIdx.y).  A warp touches 32 consecutive channels of
 // one pixel per access.  The per-channel matrices are staged transposed in shared memory ([elem][channel]).
-template <typename T, int BS>
+template <typename T, typename TO, int BS>
 __global__ void __launch_bounds__(256)
-block_transform_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C,
+block_transform_kernel(const T* __restrict__ x, TO* __restrict__ out, int B, int H, int W, int C,
                        const float* __restrict__ Tm, int per_channel, float alpha, float beta) {
     __shared__ float Ts[BS * BS][64];
     const int c = blockIdx.y * 64 + threadIdx.x;
@@ -47,7 +47,7 @@ block_transform_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int 
             for (int i = 0; i < BS; ++i) a = fmaf(Ts[u * BS + i][threadIdx.x], X[i][j], a);
             Y[u][j] = a;
         }
-    T* dst = out + (long long)b * H * W * C + c;
+    TO* dst = out + (long long)b * H * W * C + c;
 #pragma unroll
     for (int u = 0; u < BS; ++u)
 #pragma unroll
@@ -57,7 +57,7 @@ block_transform_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int 
                 float a = 0.f;
 #pragma unroll
                 for (int j = 0; j < BS; ++j) a = fmaf(Y[u][j], Ts[v * BS + j][threadIdx.x], a);
-                dst[((long long)h * W + w) * C] = from_f<T>(alpha * X[u][v] + beta * a);
+                dst[((long long)h * W + w) * C] = from_f<TO>(alpha * X[u][v] + beta * a);
             }
         }
 }
@@ -205,9 +205,9 @@ __device__ __forceinline__ void bilin_src(int d, int n_in, int n_out, int& i0, i
     lam = s - (float)i0;
 }
 
-template <typename T>
+template <typename TH, typename T>
 __global__ void __launch_bounds__(256)
-avif_combine_kernel(const T* __restrict__ hsrc, const T* __restrict__ xt, const float* __restrict__ gates,
+avif_combine_kernel(const TH* __restrict__ hsrc, const T* __restrict__ xt, const float* __restrict__ gates,
                     const T* __restrict__ color, const T* __restrict__ edge, T* __restrict__ out, int B, int H, int W,
                     int C) {
     const int cv = C >> 3;
@@ -245,11 +245,12 @@ avif_combine_kernel(const T* __restrict__ hsrc, const T* __restrict__ xt, const 
             for (int k = 0; k < 8; ++k)
                 attn[k] += hl0 * (wl0 * g00[k] + lw * g01[k]) + lh * (wl0 * g10[k] + lw * g11[k]);
         }
-        Vec8<T> hv, xv, cvv, ev;
+        Vec8<TH> hv;
+        Vec8<T> xv, cvv, ev;
         hv.load(hsrc + i * 8); xv.load(xt + i * 8); cvv.load(color + i * 8); ev.load(edge + i * 8);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hv.v[k] = hv.v[k] + xv.v[k] * (attn[k] * 0.25f) * cvv.v[k] * ev.v[k];
-        hv.store(out + i * 8);
+        for (int k = 0; k < 8; ++k) xv.v[k] = hv.v[k] + xv.v[k] * (attn[k] * 0.25f) * cvv.v[k] * ev.v[k];
+        xv.store(out + i * 8);
     }
 }
 
@@ -262,15 +263,18 @@ inline int grid_for(long long total, int block) {
 }  // namespace
 
 extern "C" int ddpmir_block_transform(const void* x, int dtype, int B, int H, int W, int C, const float* T, int bs,
-                                      int per_channel, float alpha, float beta, void* out, ddpmir_stream_t stream) {
+                                      int per_channel, float alpha, float beta, void* out, int out_dtype,
+                                      ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(x && out && T, "block_transform: null pointer");
     DDPMIR_CHECK_ARG(bs == 4 || bs == 8, "block_transform: block size %d", bs);
     const long long nblk = (long long)B * ((H + bs - 1) / bs) * ((W + bs - 1) / bs);
     dim3 grid(ceil_div(nblk, 4), ceil_div(C, 64)), block(64, 4);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(TT, BS) block_transform_kernel<TT, BS><<<grid, block, 0, st>>>((const TT*)x, (TT*)out, B, H, W, C, T, per_channel, alpha, beta)
-    if (dtype == DDPMIR_F32) { if (bs == 4) LAUNCH(float, 4); else LAUNCH(float, 8); }
-    else { if (bs == 4) LAUNCH(bf16, 4); else LAUNCH(bf16, 8); }
+#define LAUNCH(TT, TO, BS) block_transform_kernel<TT, TO, BS><<<grid, block, 0, st>>>((const TT*)x, (TO*)out, B, H, W, C, T, per_channel, alpha, beta)
+#define LAUNCH_BS(TT, TO) do { if (bs == 4) LAUNCH(TT, TO, 4); else LAUNCH(TT, TO, 8); } while (0)
+    if (dtype == DDPMIR_F32) { if (out_dtype == DDPMIR_F32) LAUNCH_BS(float, float); else LAUNCH_BS(float, bf16); }
+    else { if (out_dtype == DDPMIR_F32) LAUNCH_BS(bf16, float); else LAUNCH_BS(bf16, bf16); }
+#undef LAUNCH_BS
 #undef LAUNCH
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
@@ -316,16 +320,16 @@ extern "C" int ddpmir_avgpool_pyramid(const void* x, int dtype, int B, int H, in
     return DDPMIR_OK;
 }
 
-extern "C" int ddpmir_avif_combine(const void* h, const void* xt, const float* gates, const void* color,
+extern "C" int ddpmir_avif_combine(const void* h, int h_dtype, const void* xt, const float* gates, const void* color,
                                    const void* edge, int dtype, int B, int H, int W, int C, void* out,
                                    ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(h && xt && gates && color && edge && out && C % 8 == 0, "avif_combine: bad arguments");
     const long long total = (long long)B * H * W * (C / 8);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DDPMIR_F32)
-        avif_combine_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)h, (const float*)xt, gates, (const float*)color, (const float*)edge, (float*)out, B, H, W, C);
-    else
-        avif_combine_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)h, (const bf16*)xt, gates, (const bf16*)color, (const bf16*)edge, (bf16*)out, B, H, W, C);
+#define GO(TH, T) avif_combine_kernel<TH, T><<<grid_for(total, 256), 256, 0, st>>>((const TH*)h, (const T*)xt, gates, (const T*)color, (const T*)edge, (T*)out, B, H, W, C)
+    if (dtype == DDPMIR_F32) { DDPMIR_CHECK_ARG(h_dtype == DDPMIR_F32, "avif_combine: fp32 mode needs fp32 h"); GO(float, float); }
+    else { if (h_dtype == DDPMIR_F32) GO(float, bf16); else GO(bf16, bf16); }
+#undef GO
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

@@ -128,7 +128,7 @@ ddrm_update_kernel(const float* __restrict__ x_theta, const void* __restrict__ c
 
 extern "C" int ddpmir_ddrm_update(const float* x_theta, const void* codec, int codec_u8_hwc, const float* y,
                                   const float* z, const float* t, float* out, int B, int C, int H, int W,
-                                  float sigma_scale, float eta, float eta_b, int last_step, uint64_t seed,
+                                  double sigma_scale_d, double eta_d, double eta_b_d, int last_step, uint64_t seed,
                                   uint32_t step, uint64_t noise_offset, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(x_theta && codec && y && t && out, "ddrm_update: null pointer");
     DDPMIR_CHECK_ARG(noise_offset % 4 == 0, "ddrm_update: noise_offset must be a multiple of 4");
@@ -140,7 +140,9 @@ extern "C" int ddpmir_ddrm_update(const float* x_theta, const void* codec, int c
     int grid = (int)((groups + 255) / 256);
     const int cap = 148 * 16;
     if (grid > cap) grid = cap;
-    const float om = (float)(1.0 - (double)eta_b);
+    // Python-side scalars are doubles; the reference's tensor ops round each of them to fp32 once
+    const float sigma_scale = (float)sigma_scale_d, eta = (float)eta_d, eta_b = (float)eta_b_d;
+    const float om = (float)(1.0 - eta_b_d);
     if (codec_u8_hwc)
         ddrm_update_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x_theta, codec, y, z, t, out, per_image, C,
                                                                        (int)HW, B, sigma_scale, eta, eta_b, om,

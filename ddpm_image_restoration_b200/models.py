@@ -228,7 +228,7 @@ class _RestorationUNet(nn.Module):
 
     def _forward(self, x, t, level, taps=None):
         fam = _FAMILY[self.family]
-        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32   # GEMM operand dtype
         P = self.prepack()
         sd = dict(self.named_parameters())
         sd.update(dict(self.named_buffers()))
@@ -259,46 +259,58 @@ class _RestorationUNet(nn.Module):
         if taps is not None:
             taps.update(t_emb=t_emb, d1=d1, d2=d2, d3=d3, d4=d4, d5=d5, bn=bn, u1=u1, u2=u2, u3=u3, u4=u4, u5=u5)
         if self.family == "avif":
-            tr = ops.block_transform(u5, sd["avif_layer.transform_weights"], 0.0, 1.0)
+            tr = ops.block_transform(u5, sd["avif_layer.transform_weights"], 0.0, 1.0, out_dtype=dt)
             q1 = ops.gemm(tr, P["tail_q0_w"], 64, self.impl, bias=sd["avif_layer.quantization.0.bias"], act=ops.ACT_RELU)
             tail = torch.full((B,), fam["tail"], dtype=torch.float32, device=x.device)
-            comb = ops.gemm(q1, P["tail_q2_w"], 64, self.impl, bias=sd["avif_layer.quantization.2.bias"],
-                            act=ops.ACT_SIGMOID, img_scale=tail, mul=tr, res=u5)
+            comb = ops.gemm(q1, P["tail_q2_w"], 64, self.impl, out_dtype=torch.float32,
+                            bias=sd["avif_layer.quantization.2.bias"], act=ops.ACT_SIGMOID, img_scale=tail, mul=tr, res=u5)
         else:
             comb = ops.block_transform(u5, sd["dct_layer.dct_matrix"], 1.0, fam["tail"])
         st = ops.groupnorm_stats(comb, 8)
-        a = ops.groupnorm_apply(comb, st, sd["out_conv.0.weight"], sd["out_conv.0.bias"], ops.ACT_SILU)
+        a = ops.groupnorm_apply(comb, st, sd["out_conv.0.weight"], sd["out_conv.0.bias"], ops.ACT_SILU, out_dtype=dt)
         return ops.out_conv_tanh(a, sd["out_conv.2.weight"], sd["out_conv.2.bias"])
 
     def _block(self, p, x, t_emb, boosts, sd, W, dt):
-        """{WebP,JPEG,AVIF}ResAttnBlock.forward (webp_inference.py:303-327) on NHWC activations."""
+        """{WebP,JPEG,AVIF}ResAttnBlock.forward (webp_inference.py:303-327) on NHWC activations.
+
+        Two tensor classes: the *stream* (block inputs/outputs, conv outputs feeding GroupNorm, the attention and
+        shortcut residuals) stays fp32 -- only element-wise / normalisation kernels read it -- while every GEMM
+        operand is written in `dt` (bf16 in production) by the kernel that produces it.  Keeping the stream in fp32
+        removes the largest avoidable share of the bf16 error budget ("error budget")."""
         fam = _FAMILY[self.family]
         impl = self.impl
-        first = x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.float32 and p == "down1"
+        f32 = torch.float32
+        first = p == "down1"
         co = sd[f"{p}.conv1.bias"].shape[0]
         tb = ops.linear_rows(t_emb, sd[f"{p}.time_proj.weight"], sd[f"{p}.time_proj.bias"])
         if first:
             st = ops.groupnorm_stats(x, 3, nchw=True)
-            h1 = ops.conv_input(x, W["conv1_w"], sd[f"{p}.conv1.bias"], dt, st, sd[f"{p}.norm1.weight"],
+            h1 = ops.conv_input(x, W["conv1_w"], sd[f"{p}.conv1.bias"], f32, st, sd[f"{p}.norm1.weight"],
                                 sd[f"{p}.norm1.bias"], row_bias=tb)
-            sc = ops.conv_input(x, W["sc_w"], sd[f"{p}.shortcut.bias"], dt)
+            sc = ops.conv_input(x, W["sc_w"], sd[f"{p}.shortcut.bias"], f32)
         else:
             ci = x.shape[-1]
             st = ops.groupnorm_stats(x, _groups(ci))
-            a = ops.groupnorm_apply(x, st, sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], ops.ACT_NONE)
-            h1 = ops.conv3x3(a, W["conv1_w"], co, impl, bias=sd[f"{p}.conv1.bias"], row_bias=tb)
-            sc = ops.gemm(x, W["sc_w"], co, impl, bias=sd[f"{p}.shortcut.bias"]) if "sc_w" in W else x
+            if "sc_w" in W:
+                a, x_op = ops.groupnorm_apply(x, st, sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], ops.ACT_NONE,
+                                              out_dtype=dt, raw_copy=True)
+                sc = ops.gemm(x_op, W["sc_w"], co, impl, out_dtype=f32, bias=sd[f"{p}.shortcut.bias"])
+            else:
+                a = ops.groupnorm_apply(x, st, sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], ops.ACT_NONE, out_dtype=dt)
+                sc = x
+            h1 = ops.conv3x3(a, W["conv1_w"], co, impl, out_dtype=f32, bias=sd[f"{p}.conv1.bias"], row_bias=tb)
         st = ops.groupnorm_stats(h1, _groups(co))
-        a = ops.groupnorm_apply(h1, st, sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ops.ACT_GELU)
-        h2 = ops.conv3x3(a, W["conv2_w"], co, impl, bias=sd[f"{p}.conv2.bias"])
+        a = ops.groupnorm_apply(h1, st, sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ops.ACT_GELU, out_dtype=dt)
+        h2, h2_op = ops.conv3x3(a, W["conv2_w"], co, impl, out_dtype=f32, out2_dtype=dt, bias=sd[f"{p}.conv2.bias"])
         Bn, H, Wd, _ = h2.shape
-        qkv = ops.gemm(h2, W["in_w"], 3 * co, impl, bias=sd[f"{p}.attn.in_proj_bias"])
+        qkv = ops.gemm(h2_op, W["in_w"], 3 * co, impl, bias=sd[f"{p}.attn.in_proj_bias"])
         ao = ops.attention(qkv.view(Bn, H * Wd, 3 * co), fam["heads"], impl).view(Bn, H, Wd, co)
-        h3 = ops.gemm(ao, W["out_w"], co, impl, bias=sd[f"{p}.attn.out_proj.bias"], res=h2)
         f = f"{p}.freq_guide"
         if self.family == "avif":
+            h3, h3_op = ops.gemm(ao, W["out_w"], co, impl, out_dtype=f32, out2_dtype=dt,
+                                 bias=sd[f"{p}.attn.out_proj.bias"], res=h2)
             a_ = f"{f}.adaptive_transform"
-            tr = ops.block_transform(h3, sd[f"{a_}.transform_weights"], 0.0, 1.0)
+            tr = ops.block_transform(h3, sd[f"{a_}.transform_weights"], 0.0, 1.0, out_dtype=dt)
             q1 = ops.gemm(tr, W["q0_w"], co, impl, bias=sd[f"{a_}.quantization.0.bias"], act=ops.ACT_RELU)
             xt = ops.gemm(q1, W["q2_w"], co, impl, bias=sd[f"{a_}.quantization.2.bias"], act=ops.ACT_SIGMOID, mul=tr)
             pooled = ops.avgpool_pyramid(h3)                       # [85, B, C] fp32
@@ -310,21 +322,22 @@ class _RestorationUNet(nn.Module):
                 ops.linear_rows(hid, W[f"ms{i}_w3"], sd[f"{f}.multi_scale_attn.{i}.3.bias"], ops.ACT_SIGMOID,
                                 out=gates[off:off + s * s])
                 off += s * s
-            c1 = ops.gemm(h3, W["c0_w"], co, impl, bias=sd[f"{f}.color_consistency.0.bias"], act=ops.ACT_RELU)
+            c1 = ops.gemm(h3_op, W["c0_w"], co, impl, bias=sd[f"{f}.color_consistency.0.bias"], act=ops.ACT_RELU)
             color = ops.gemm(c1, W["c2_w"], co, impl, bias=sd[f"{f}.color_consistency.2.bias"], act=ops.ACT_SIGMOID,
                              img_scale=boosts[0])
-            e1 = ops.conv3x3(h3, W["e0_w"], co // 2, impl, bias=sd[f"{f}.edge_preserve.0.bias"], act=ops.ACT_RELU)
+            e1 = ops.conv3x3(h3_op, W["e0_w"], co // 2, impl, bias=sd[f"{f}.edge_preserve.0.bias"], act=ops.ACT_RELU)
             edge = ops.conv3x3(e1, W["e2_w"], co, impl, bias=sd[f"{f}.edge_preserve.2.bias"], act=ops.ACT_SIGMOID,
                                img_scale=boosts[1])
             e = ops.avif_combine(h3, xt, gates, color, edge)
         else:
-            d = ops.block_transform(h3, sd[f"{f}.dct.dct_matrix"], 0.0, 1.0)
+            h3 = ops.gemm(ao, W["out_w"], co, impl, out_dtype=f32, bias=sd[f"{p}.attn.out_proj.bias"], res=h2)
+            d = ops.block_transform(h3, sd[f"{f}.dct.dct_matrix"], 0.0, 1.0, out_dtype=dt)
             g1 = ops.gemm(d, W["g1_w"], co, impl, bias=W["g1_b"], act=ops.ACT_LRELU02, freq_mode=1, bs=fam["bs"],
                           low=fam["low"])
             e = ops.gemm(g1, W["g2_w"], co, impl, bias=sd[f"{f}.low_freq_attn.2.bias"],
                          bias2=sd[f"{f}.high_freq_attn.2.bias"], act=ops.ACT_SIGMOID, freq_mode=2, bs=fam["bs"],
                          low=fam["low"], img_scale=boosts[0], mul=d, res=h3)
-        return ops.conv3x3(e, W["fo_w"], co, impl, bias=sd[f"{f}.conv_out.bias"], res=sc)
+        return ops.conv3x3(e, W["fo_w"], co, impl, out_dtype=f32, bias=sd[f"{f}.conv_out.bias"], res=sc)
 
 
 class WebPDiffusionModel(_RestorationUNet):

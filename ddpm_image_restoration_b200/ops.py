@@ -14,6 +14,46 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- instrumentation (bench.py): kernel-launch counter and CUDA-event timing of selected ops ----------------
+LAUNCHES = [0]          # kernels of libddpmir.so launched through this module
+_TIMED = {}             # op name -> list of (start_event, end_event, tag)
+_TIMED_FILTER = None    # callable(name, tag) -> bool, or None
+
+
+def timing_begin(filter_fn):
+    global _TIMED_FILTER
+    _TIMED.clear()
+    _TIMED_FILTER = filter_fn
+
+
+def timing_end():
+    """Returns {name: [(milliseconds, tag), ...]}; call after torch.cuda.synchronize()."""
+    global _TIMED_FILTER
+    _TIMED_FILTER = None
+    out = {k: [(s.elapsed_time(e), tag) for s, e, tag in v] for k, v in _TIMED.items()}
+    _TIMED.clear()
+    return out
+
+
+class _timed:
+    def __init__(self, name, tag, launches):
+        self.name, self.tag = name, tag
+        LAUNCHES[0] += launches
+        self.on = _TIMED_FILTER is not None and _TIMED_FILTER(name, tag)
+
+    def __enter__(self):
+        if self.on:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e.record()
+            _TIMED.setdefault(self.name, []).append((self.s, self.e, self.tag))
+
+
 def _p(t):
     if t is None:
         return None
@@ -54,6 +94,7 @@ def ddrm_update(x_theta, codec, y, t, sigma_scale, eta=0.85, eta_b=1.0, z=None, 
                                        float(sigma_scale), float(eta), float(eta_b), int(last_step), int(seed),
                                        int(step), int(noise_offset), _stream())
     _lib.check(rc, "ddrm_update")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -63,6 +104,7 @@ def gmm_update(x_t, pred, y=None, svd_prior=None, g=0.0, z=None, use_first=True,
     rc = _lib.lib().ddpmir_gmm_update(_p(x_t), _p(pred), _p(y), _p(svd_prior), float(g), _p(z), _p(out), x_t.numel(),
                                       int(use_first), float(noise_scale), int(last_step), int(seed), int(step), _stream())
     _lib.check(rc, "gmm_update")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -71,12 +113,14 @@ def lincomb(a, wa, b=None, wb=0.0, z=None, sigma=0.0, seed=0, step=0):
     rc = _lib.lib().ddpmir_lincomb(_p(a), float(wa), _p(b), float(wb), _p(z), float(sigma), _p(out), a.numel(), int(seed),
                                    int(step), _stream())
     _lib.check(rc, "lincomb")
+    LAUNCHES[0] += 1
     return out
 
 
 def philox_normal(shape, seed, step, device="cuda"):
     out = torch.empty(shape, dtype=torch.float32, device=device)
     _lib.check(_lib.lib().ddpmir_philox_normal(_p(out), out.numel(), int(seed), int(step), _stream()), "philox_normal")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -85,6 +129,7 @@ def u8_hwc_to_nchw(u8):
     B, H, W, C = u8.shape
     out = torch.empty((B, C, H, W), dtype=torch.float32, device=u8.device)
     _lib.check(_lib.lib().ddpmir_u8_hwc_to_nchw(_p(u8), _p(out), B, C, H, W, _stream()), "u8_hwc_to_nchw")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -92,6 +137,7 @@ def quantize_u8_hwc(x, out=None):
     B, C, H, W = x.shape
     out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device) if out is None else out
     _lib.check(_lib.lib().ddpmir_quantize_u8_hwc(_p(_f32(x, "x")), _p(out), B, C, H, W, _stream()), "quantize_u8_hwc")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -101,6 +147,7 @@ def phase_reference(ref):
     ws = torch.empty_like(phasor)
     _lib.check(_lib.lib().ddpmir_phase_reference(_p(_f32(ref, "ref")), B * C, H, W, _p(phasor), _p(ws), _stream()),
                "phase_reference")
+    LAUNCHES[0] += 2
     return phasor
 
 
@@ -110,15 +157,17 @@ def phase_consistency_cached(x, phasor, alpha):
     ws = torch.empty((B * C, H, W, 2), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().ddpmir_phase_consistency(_p(_f32(x, "x")), _p(phasor), float(alpha), B * C, H, W, _p(out), _p(ws),
                                                    _stream()), "phase_consistency")
+    LAUNCHES[0] += 3
     return out
 
 
 def svd_lowrank(x, k, sweeps=0):
     B, C, H, W = x.shape
     out = torch.empty_like(x)
-    ws = torch.empty((B * C * (H * W + 2 * H),), dtype=torch.float32, device=x.device)
+    ws = torch.empty((B * C * (H * W + H * H + 2 * H),), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().ddpmir_svd_lowrank(_p(_f32(x, "x")), B * C, H, W, int(k), _p(out), _p(ws), int(sweeps), _stream()),
                "svd_lowrank")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -130,6 +179,7 @@ def color_l1(pred, target):
     ws = torch.empty((3,), dtype=torch.float64, device=pred.device)
     _lib.check(_lib.lib().ddpmir_color_l1(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B, H, W, _p(out), _p(ws),
                                           _stream()), "color_l1")
+    LAUNCHES[0] += 2
     return out[0]
 
 
@@ -142,6 +192,7 @@ def time_embed(t, w0, b0, w1, b1):
     out = torch.empty((B, dim), dtype=torch.float32, device=t.device)
     _lib.check(_lib.lib().ddpmir_time_embed(_p(_f32(t, "t")), B, dim, _p(w0), _p(b0), _p(w1), _p(b1), _p(ws), _p(out),
                                             _stream()), "time_embed")
+    LAUNCHES[0] += 3
     return out
 
 
@@ -154,6 +205,7 @@ def linear_rows(x, w, bias, act=ACT_NONE, out=None):
         raise _lib.DdpmirError("linear_rows: bad out tensor")
     _lib.check(_lib.lib().ddpmir_linear_rows(_p(_f32(x, "x")), rows, K, _p(_f32(w, "w")), _p(bias), N, act, _p(out),
                                              _stream()), "linear_rows")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -168,15 +220,21 @@ def groupnorm_stats(x, groups, eps=1e-5, nchw=False):
     ws = torch.empty((B * groups * 2,), dtype=torch.float64, device=x.device)
     _lib.check(_lib.lib().ddpmir_groupnorm_stats(_p(x), _code(x.dtype), int(nchw), B, HW, C, groups, float(eps), _p(mr),
                                                  _p(ws), _stream()), "groupnorm_stats")
+    LAUNCHES[0] += 2
     return mr
 
 
-def groupnorm_apply(x, mean_rstd, gamma, beta, act=ACT_NONE):
+def groupnorm_apply(x, mean_rstd, gamma, beta, act=ACT_NONE, out_dtype=None, raw_copy=False):
+    """Returns act(GN(x)) in out_dtype; with raw_copy=True also x itself cast to out_dtype (GEMM operand copy)."""
     B, H, W, C = x.shape
-    out = torch.empty_like(x)
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    raw = torch.empty(x.shape, dtype=out_dtype, device=x.device) if raw_copy else None
     _lib.check(_lib.lib().ddpmir_groupnorm_apply(_p(x), _code(x.dtype), B, H * W, C, mean_rstd.shape[1], _p(mean_rstd),
-                                                 _p(gamma), _p(beta), act, _p(out), _stream()), "groupnorm_apply")
-    return out
+                                                 _p(gamma), _p(beta), act, _p(out), _code(out_dtype), _p(raw), _stream()),
+               "groupnorm_apply")
+    LAUNCHES[0] += 1
+    return (out, raw) if raw_copy else out
 
 
 def conv_input(x, w, bias, out_dtype, mean_rstd=None, gamma=None, beta=None, row_bias=None):
@@ -186,40 +244,48 @@ def conv_input(x, w, bias, out_dtype, mean_rstd=None, gamma=None, beta=None, row
     _lib.check(_lib.lib().ddpmir_conv_input(_p(_f32(x, "x")), B, Cin, H, W, _p(mean_rstd), _p(gamma), _p(beta), _p(_f32(w, "w")),
                                             _p(bias), _p(row_bias), N, ks, _code(out_dtype), _p(out), _stream()),
                "conv_input")
+    LAUNCHES[0] += 1
     return out
 
 
-def _epi(bias=None, bias2=None, row_bias=None, img_scale=None, mul=None, res=None, act=ACT_NONE, freq_mode=0, bs=0, low=0):
+def _epi(out_dtype, out2=None, bias=None, bias2=None, row_bias=None, img_scale=None, mul=None, res=None, act=ACT_NONE,
+         freq_mode=0, bs=0, low=0):
     def a(t):
         return None if t is None else t.data_ptr()
-    for t in (bias, bias2, row_bias, img_scale, mul, res):
+    for t in (bias, bias2, row_bias, img_scale, mul, res, out2):
         if t is not None and (not t.is_cuda or not t.is_contiguous()):
             raise _lib.DdpmirError("epilogue tensors must be contiguous CUDA tensors")
-    return Epilogue(a(bias), a(bias2), a(row_bias), a(img_scale), a(mul), a(res), act, freq_mode, bs, low)
+    for t in (bias, bias2, row_bias, img_scale):
+        _f32(t, "epilogue vector")
+    dt = lambda t: F32 if t is None else _code(t.dtype)
+    return Epilogue(a(bias), a(bias2), a(row_bias), a(img_scale), a(mul), a(res), a(out2), act, freq_mode, bs, low,
+                    _code(out_dtype), dt(out2), dt(mul), dt(res))
 
 
-def conv3x3(x, w, N, impl=IMPL_AUTO, **epi):
-    """x [B,H,W,Cin]; w packed [N, 9*Cin] (kh,kw,cin) in x.dtype."""
-    B, H, W, Cin = x.shape
-    if w.dtype != x.dtype or w.numel() != N * 9 * Cin:
-        raise _lib.DdpmirError("conv3x3: weight must be packed [N, 9*Cin] in the activation dtype")
-    out = torch.empty((B, H, W, N), dtype=x.dtype, device=x.device)
-    e = _epi(**epi)
-    _lib.check(_lib.lib().ddpmir_conv3x3(_p(x), _code(x.dtype), B, H, W, Cin, _p(w), N, ctypes.byref(e), _p(out), impl,
-                                         _stream()), "conv3x3")
-    return out
-
-
-def gemm(x, w, N, impl=IMPL_AUTO, **epi):
-    """x [B,H,W,K]; w [N,K] in x.dtype."""
+def _igemm(kind, x, w, N, impl, out_dtype, out2_dtype, epi):
     B, H, W, K = x.shape
-    if w.dtype != x.dtype or w.numel() != N * K:
-        raise _lib.DdpmirError("gemm: weight must be [N, K] in the activation dtype")
-    out = torch.empty((B, H, W, N), dtype=x.dtype, device=x.device)
-    e = _epi(**epi)
-    _lib.check(_lib.lib().ddpmir_gemm(_p(x), _code(x.dtype), B, H, W, K, _p(w), N, ctypes.byref(e), _p(out), impl, _stream()),
-               "gemm")
-    return out
+    taps = 9 if kind == "conv3x3" else 1
+    if w.dtype != x.dtype or w.numel() != N * taps * K:
+        raise _lib.DdpmirError(f"{kind}: weight must be packed [N, {taps}*K] in the operand dtype")
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    out = torch.empty((B, H, W, N), dtype=out_dtype, device=x.device)
+    out2 = torch.empty((B, H, W, N), dtype=out2_dtype, device=x.device) if out2_dtype is not None else None
+    e = _epi(out_dtype, out2, **epi)
+    fn = _lib.lib().ddpmir_conv3x3 if taps == 9 else _lib.lib().ddpmir_gemm
+    with _timed(kind, (B, H, W, K, N), 1):
+        _lib.check(fn(_p(x), _code(x.dtype), B, H, W, K, _p(w), N, ctypes.byref(e), _p(out), impl, _stream()), kind)
+    return out if out2 is None else (out, out2)
+
+
+def conv3x3(x, w, N, impl=IMPL_AUTO, out_dtype=None, out2_dtype=None, **epi):
+    """x [B,H,W,Cin] (operand dtype); w packed [N, 9*Cin] (kh,kw,cin) in x.dtype.  Returns out (out_dtype, default
+    x.dtype) or (out, out2) when out2_dtype is given."""
+    return _igemm("conv3x3", x, w, N, impl, out_dtype, out2_dtype, epi)
+
+
+def gemm(x, w, N, impl=IMPL_AUTO, out_dtype=None, out2_dtype=None, **epi):
+    """x [B,H,W,K]; w [N,K] in x.dtype."""
+    return _igemm("gemm", x, w, N, impl, out_dtype, out2_dtype, epi)
 
 
 def attention(qkv, heads, impl=IMPL_AUTO):
@@ -227,16 +293,21 @@ def attention(qkv, heads, impl=IMPL_AUTO):
     B, L, C3 = qkv.shape
     C = C3 // 3
     out = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)
-    _lib.check(_lib.lib().ddpmir_attention(_p(qkv), _code(qkv.dtype), B, L, C, heads, _p(out), impl, _stream()), "attention")
+    with _timed("attention", (B, L, C, heads), 1):
+        _lib.check(_lib.lib().ddpmir_attention(_p(qkv), _code(qkv.dtype), B, L, C, heads, _p(out), impl, _stream()),
+                   "attention")
     return out
 
 
-def block_transform(x, T, alpha=0.0, beta=1.0):
+def block_transform(x, T, alpha=0.0, beta=1.0, out_dtype=None):
     B, H, W, C = x.shape
     bs = T.shape[-1]
-    out = torch.empty_like(x)
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     _lib.check(_lib.lib().ddpmir_block_transform(_p(x), _code(x.dtype), B, H, W, C, _p(_f32(T, "T")), bs, int(T.dim() == 3),
-                                                 float(alpha), float(beta), _p(out), _stream()), "block_transform")
+                                                 float(alpha), float(beta), _p(out), _code(out_dtype), _stream()),
+               "block_transform")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -244,6 +315,7 @@ def maxpool2(x):
     B, H, W, C = x.shape
     out = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
     _lib.check(_lib.lib().ddpmir_maxpool2(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "maxpool2")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -253,6 +325,7 @@ def upsample2_concat(lo, skip):
     out = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=lo.dtype, device=lo.device)
     _lib.check(_lib.lib().ddpmir_upsample2_concat(_p(lo), _p(skip), _code(lo.dtype), B, H, W, C1, C2, _p(out), _stream()),
                "upsample2_concat")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -260,14 +333,17 @@ def avgpool_pyramid(x):
     B, H, W, C = x.shape
     out = torch.empty((85, B, C), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().ddpmir_avgpool_pyramid(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "avgpool_pyramid")
+    LAUNCHES[0] += 2
     return out
 
 
 def avif_combine(h, xt, gates, color, edge):
+    """h may be the fp32 stream while xt/color/edge (and the result) are in the operand dtype."""
     B, H, W, C = h.shape
-    out = torch.empty_like(h)
-    _lib.check(_lib.lib().ddpmir_avif_combine(_p(h), _p(xt), _p(_f32(gates, "gates")), _p(color), _p(edge), _code(h.dtype), B, H,
-                                              W, C, _p(out), _stream()), "avif_combine")
+    out = torch.empty(h.shape, dtype=xt.dtype, device=h.device)
+    _lib.check(_lib.lib().ddpmir_avif_combine(_p(h), _code(h.dtype), _p(xt), _p(_f32(gates, "gates")), _p(color), _p(edge),
+                                              _code(xt.dtype), B, H, W, C, _p(out), _stream()), "avif_combine")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -277,10 +353,12 @@ def out_conv_tanh(x, w, bias):
     out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().ddpmir_out_conv_tanh(_p(x), _code(x.dtype), B, H, W, Cin, _p(_f32(w, "w")), _p(bias), N, _p(out),
                                                _stream()), "out_conv_tanh")
+    LAUNCHES[0] += 1
     return out
 
 
 def cast_bf16(x):
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.check(_lib.lib().ddpmir_cast_f32_to_bf16(_p(_f32(x, "x")), _p(out), x.numel(), _stream()), "cast_bf16")
+    LAUNCHES[0] += 1
     return out

@@ -45,64 +45,85 @@ class _DDRMSampler:
         size = (B + n - 1) // n
         return [(s, min(B, s + size)) for s in range(0, B, size)]
 
-    def sample(self, x_t, quality, steps=100, eta=0.85, eta_b=1.0):
+    def begin(self, x_t, quality, steps=100, eta=0.85, eta_b=1.0):
+        """Set up one trajectory (staging buffers, cached reference phasors); returns the mutable state."""
         cfg = _DDRM[self.family]
         if not x_t.is_cuda:
             raise RuntimeError("the B200 sampler runs on CUDA only (no CPU fallback)")
         self.model.eval()
         dev = x_t.device
         x_t = x_t.contiguous().float().clone()
-        y = x_t.clone()
         B, C, H, W = x_t.shape
         chunks = self._chunks(B)
         use_phase = quality < cfg["q_thr"]
-        phasor = ops.phase_reference(y) if (use_phase and steps > cfg["period"]) else None
+        st = dict(cfg=cfg, x_t=x_t, y=x_t.clone(), quality=quality, steps=steps, eta=eta, eta_b=eta_b, chunks=chunks,
+                  use_phase=use_phase, h2d=0, d2h=0, codec_s=0.0,
+                  phasor=ops.phase_reference(x_t) if (use_phase and steps > cfg["period"]) else None)
         # staging: device uint8 buffers and pinned host buffers, one set per micro-batch
-        dev_u8 = [torch.empty((e - s, H, W, C), dtype=torch.uint8, device=dev) for s, e in chunks]
-        pin_src = [torch.empty((e - s, H, W, C), dtype=torch.uint8, pin_memory=True) for s, e in chunks]
-        pin_dst = [torch.empty((e - s, H, W, C), dtype=torch.uint8, pin_memory=True) for s, e in chunks]
-        dev_dec = [torch.empty((e - s, H, W, C), dtype=torch.uint8, device=dev) for s, e in chunks]
-        events = [torch.cuda.Event() for _ in chunks]
-        h2d = d2h = 0
+        mk = lambda s, e, **kw: torch.empty((e - s, H, W, C), dtype=torch.uint8, **kw)
+        st["dev_u8"] = [mk(s, e, device=dev) for s, e in chunks]
+        st["pin_src"] = [mk(s, e, pin_memory=True) for s, e in chunks]
+        st["pin_dst"] = [mk(s, e, pin_memory=True) for s, e in chunks]
+        st["dev_dec"] = [mk(s, e, device=dev) for s, e in chunks]
+        st["events"] = [torch.cuda.Event() for _ in chunks]
+        return st
+
+    def step(self, st, i):
+        """One sampler timestep i (steps-1 ... 0) over the whole batch: webp_inference.py:566-600."""
+        import time
+        cfg, x_t, y, chunks = st["cfg"], st["x_t"], st["y"], st["chunks"]
+        B, C, H, W = x_t.shape
+        dev = x_t.device
+        t_val = float(i) / st["steps"]
+        x_next = torch.empty(x_t.shape, dtype=torch.float32, device=dev)
+        thetas = []
         with torch.no_grad():
-            for i in range(steps - 1, -1, -1):
-                t_val = float(i) / steps
-                x_next = torch.empty_like(x_t)
-                thetas = []
-                # phase 1: enqueue all GPU work of this timestep (UNet + quantise + D2H) per micro-batch
-                for k, (s, e) in enumerate(chunks):
-                    t = torch.full((e - s,), t_val, dtype=torch.float32, device=dev)
-                    x_theta = self.model(x_t[s:e], t, t)
-                    ops.quantize_u8_hwc(x_theta, out=dev_u8[k])
-                    pin_src[k].copy_(dev_u8[k], non_blocking=True)
-                    events[k].record()
-                    thetas.append((x_theta, t))
-                    d2h += dev_u8[k].numel()
-                # phase 2: as each micro-batch lands on the host, fan its images out to the codec pool
-                futures = []
-                for k in range(len(chunks)):
-                    events[k].synchronize()
-                    futures.append(_codec.submit_roundtrip(cfg["codec"], quality, pin_src[k].numpy(), pin_dst[k].numpy()))
-                # phase 3: decoded pixels back to the device, fused update
-                for k, (s, e) in enumerate(chunks):
-                    for f in futures[k]:
-                        f.result()
-                    dev_dec[k].copy_(pin_dst[k], non_blocking=True)
-                    h2d += pin_dst[k].numel()
-                    x_theta, t = thetas[k]
-                    z = None
-                    if self.noise_fn is not None and i > 0:
-                        z = self.noise_fn(i, x_t)[s:e].contiguous()
-                    # the flat NCHW element index inside the FULL batch keys the noise (noise_offset), so the result
-                    # does not depend on the micro-batch split
-                    ops.ddrm_update(x_theta, dev_dec[k], y[s:e], t, cfg["sigma"], eta, eta_b, z=z, last_step=(i == 0),
-                                    seed=self.seed, step=i, out=x_next[s:e], noise_offset=s * C * H * W)
-                x_t = x_next
-                if i > 0 and use_phase and i % cfg["period"] == 0:
-                    x_t = ops.phase_consistency_cached(x_t, phasor, cfg["alpha"])
-        self.last_stats = dict(h2d_bytes=h2d, d2h_bytes=d2h, steps=steps, micro_batches=len(chunks),
-                               codec_threads=_codec.pool_threads())
-        return x_t
+            # phase 1: enqueue all GPU work of this timestep (UNet + quantise + D2H) per micro-batch
+            for k, (s, e) in enumerate(chunks):
+                t = torch.full((e - s,), t_val, dtype=torch.float32, device=dev)
+                x_theta = self.model(x_t[s:e], t, t)
+                ops.quantize_u8_hwc(x_theta, out=st["dev_u8"][k])
+                st["pin_src"][k].copy_(st["dev_u8"][k], non_blocking=True)
+                st["events"][k].record()
+                thetas.append((x_theta, t))
+                st["d2h"] += st["dev_u8"][k].numel()
+            # phase 2: as each micro-batch lands on the host, fan its images out to the codec pool
+            futures = []
+            for k in range(len(chunks)):
+                st["events"][k].synchronize()
+                if k == 0:
+                    t0 = time.perf_counter()
+                futures.append(_codec.submit_roundtrip(cfg["codec"], st["quality"], st["pin_src"][k].numpy(),
+                                                       st["pin_dst"][k].numpy()))
+            # phase 3: decoded pixels back to the device, fused update
+            for k, (s, e) in enumerate(chunks):
+                for f in futures[k]:
+                    f.result()
+                if k == len(chunks) - 1:
+                    st["codec_s"] += time.perf_counter() - t0
+                st["dev_dec"][k].copy_(st["pin_dst"][k], non_blocking=True)
+                st["h2d"] += st["pin_dst"][k].numel()
+                x_theta, t = thetas[k]
+                z = None
+                if self.noise_fn is not None and i > 0:
+                    z = self.noise_fn(i, x_t)[s:e].contiguous()
+                # the flat NCHW element index inside the FULL batch keys the noise (noise_offset), so the result
+                # does not depend on the micro-batch split
+                ops.ddrm_update(x_theta, st["dev_dec"][k], y[s:e], t, cfg["sigma"], st["eta"], st["eta_b"], z=z,
+                                last_step=(i == 0), seed=self.seed, step=i, out=x_next[s:e],
+                                noise_offset=s * C * H * W)
+            if i > 0 and st["use_phase"] and i % cfg["period"] == 0:
+                x_next = ops.phase_consistency_cached(x_next, st["phasor"], cfg["alpha"])
+        st["x_t"] = x_next
+        return x_next
+
+    def sample(self, x_t, quality, steps=100, eta=0.85, eta_b=1.0):
+        st = self.begin(x_t, quality, steps, eta, eta_b)
+        for i in range(steps - 1, -1, -1):
+            self.step(st, i)
+        self.last_stats = dict(h2d_bytes=st["h2d"], d2h_bytes=st["d2h"], steps=steps, micro_batches=len(st["chunks"]),
+                               codec_threads=_codec.pool_threads(), codec_seconds=st["codec_s"])
+        return st["x_t"]
 
 
 class DDRMWebPSampler(_DDRMSampler):

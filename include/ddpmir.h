@@ -65,10 +65,11 @@ const char* ddpmir_last_error(void);
  * (codec_u8_hwc = 1; converted as ToTensor + sub(0.5).mul(2.0) would, webp_inference.py:524-528).
  * z == NULL: z is generated in-kernel, Philox4x32-10 keyed by (seed, step, noise_offset + flat NCHW element index)
  * -- see ddpmir_philox_normal; noise_offset (a multiple of 4) lets a micro-batch address its slice of the
- * whole-batch noise stream.  t is [B]. */
+ * whole-batch noise stream.  t is [B].  The scalars arrive as the Python doubles of the reference's signature and
+ * are rounded to fp32 exactly where its tensor ops would ((1-eta_b) is formed in double first). */
 int ddpmir_ddrm_update(const float* x_theta, const void* codec, int codec_u8_hwc, const float* y, const float* z,
-                       const float* t, float* out, int B, int C, int H, int W, float sigma_scale, float eta,
-                       float eta_b, int last_step, uint64_t seed, uint32_t step, uint64_t noise_offset,
+                       const float* t, float* out, int B, int C, int H, int W, double sigma_scale, double eta,
+                       double eta_b, int last_step, uint64_t seed, uint32_t step, uint64_t noise_offset,
                        ddpmir_stream_t stream);
 
 /* GaussianMixtureSampler step, 0409_method.ipynb#c1:L411-447:
@@ -108,7 +109,8 @@ int ddpmir_phase_consistency(const float* x, const float* phasor, float alpha, i
                              float* out, float* ws, ddpmir_stream_t stream);
 
 /* svd_structure_preservation, 0409_method.ipynb#c0:L321-346: rank-k truncation of every [H, W] plane
- * (one-sided Jacobi on the rows).  ws: planes * (H*W + 2*H) floats.  out may alias nothing. */
+ * (one-sided Jacobi on the rows, one CTA per plane).  ws: planes * (H*W + H*H + 2*H) floats.  sweeps <= 0 -> 30
+ * (it stops early once every row pair is orthogonal to fp32 round-off). */
 int ddpmir_svd_lowrank(const float* x, int planes, int H, int W, int k, float* out, float* ws, int sweeps,
                        ddpmir_stream_t stream);
 
@@ -139,9 +141,11 @@ int ddpmir_groupnorm_stats(const void* x, int dtype, int nchw, int B, int HW, in
                            float* mean_rstd, double* ws, ddpmir_stream_t stream);
 
 /* y = act((x - mean) * rstd * gamma[c] + beta[c]) on NHWC; act in {NONE, GELU, SILU} (webp_inference.py:304,
- * 311-312, 363-364). */
+ * 311-312, 363-364).  x in `dtype`, out in `out_dtype`; raw_copy (optional, out_dtype) receives x itself cast to
+ * out_dtype -- the operand copy of the fp32 residual stream that the 1x1 shortcut GEMM consumes. */
 int ddpmir_groupnorm_apply(const void* x, int dtype, int B, int HW, int C, int G, const float* mean_rstd,
-                           const float* gamma, const float* beta, int act, void* out, ddpmir_stream_t stream);
+                           const float* gamma, const float* beta, int act, void* out, int out_dtype, void* raw_copy,
+                           ddpmir_stream_t stream);
 
 /* Convolution of the 3-channel NCHW fp32 network input (conv1 and the 1x1 shortcut of down1,
  * webp_inference.py:282,301,337), optionally folding norm1 (mean_rstd/gamma/beta non-NULL):
@@ -151,7 +155,11 @@ int ddpmir_conv_input(const float* x, int B, int Cin, int H, int W, const float*
                       const float* beta, const float* w, const float* bias, const float* row_bias, int N,
                       int ksize, int dtype, void* out, ddpmir_stream_t stream);
 
-/* Epilogue shared by ddpmir_conv3x3 and ddpmir_gemm; m = flat pixel index (b, h, w), n = output channel:
+/* Epilogue shared by ddpmir_conv3x3 and ddpmir_gemm; m = flat pixel index (b, h, w), n = output channel.
+ * The `dtype` argument of those functions is the OPERAND type (activations in, weights); the result can be
+ * stored as fp32 (the residual stream, which only element-wise/normalisation kernels read) and/or as bf16 (the
+ * next GEMM's operand): out in out_dtype, plus an optional second copy out2 in out2_dtype.  mul / res carry
+ * their own dtypes.  A NULL epilogue means "store acc in the operand dtype".
  *     v = acc + bias[n] (+ row_bias[b, n])                      bias2 replaces bias on high-frequency pixels (freq_mode 2)
  *     v = act(v)
  *     freq_mode 1:  v = 0 unless (n < N/2) == is_low(h, w)      hidden layer of the stacked low/high gate MLP
@@ -166,10 +174,15 @@ typedef struct {
     const float* img_scale;
     const void* mul;
     const void* res;
+    void* out2;
     int act;
     int freq_mode;
     int bs;
     int low;
+    int out_dtype;
+    int out2_dtype;
+    int mul_dtype;
+    int res_dtype;
 } ddpmir_epilogue_t;
 
 /* nn.Conv2d(Cin, N, 3, padding=1) on NHWC as an implicit GEMM (webp_inference.py:282,292,229; the AVIF edge
@@ -192,7 +205,8 @@ int ddpmir_attention(const void* qkv, int dtype, int B, int L, int C, int heads,
  * and crop back: DCTLayer.forward webp_inference.py:161-192 (per_channel = 0, T [bs,bs]) and
  * AVIFAdaptiveTransform avif_inference.py:140-177 (per_channel = 1, T [C,bs,bs]).  bs in {4, 8}. T fp32. */
 int ddpmir_block_transform(const void* x, int dtype, int B, int H, int W, int C, const float* T, int bs,
-                           int per_channel, float alpha, float beta, void* out, ddpmir_stream_t stream);
+                           int per_channel, float alpha, float beta, void* out, int out_dtype,
+                           ddpmir_stream_t stream);
 
 /* nn.MaxPool2d(2), webp_inference.py:342.  out [B, H/2, W/2, C]. */
 int ddpmir_maxpool2(const void* x, int dtype, int B, int H, int W, int C, void* out, ddpmir_stream_t stream);
@@ -211,9 +225,9 @@ int ddpmir_avgpool_pyramid(const void* x, int dtype, int B, int H, int W, int C,
 /* enhanced + residual of AVIFFreqAwareBlock.forward, avif_inference.py:226-256:
  * out = h + xt * mean_s(bilinear_up(gates_s)) * color * edge, with gates [85,B,C] fp32 the sigmoid outputs of
  * the pooled MLPs (F.interpolate(..., mode='bilinear', align_corners=False) restated in-kernel) and color/edge
- * already multiplied by their boosts. */
-int ddpmir_avif_combine(const void* h, const void* xt, const float* gates, const void* color, const void* edge,
-                        int dtype, int B, int H, int W, int C, void* out, ddpmir_stream_t stream);
+ * already multiplied by their boosts.  h is in h_dtype (the fp32 stream); xt, color, edge and out in `dtype`. */
+int ddpmir_avif_combine(const void* h, int h_dtype, const void* xt, const float* gates, const void* color,
+                        const void* edge, int dtype, int B, int H, int W, int C, void* out, ddpmir_stream_t stream);
 
 /* out_conv tail, webp_inference.py:365-366: tanh(conv3x3(x) + bias), NHWC `dtype` in, NCHW fp32 out.
  * w is the checkpoint's [3, Cin, 3, 3] fp32. */

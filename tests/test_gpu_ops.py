@@ -44,7 +44,7 @@ def test_ddrm_update_bit_exact(ops, golden):
     assert torch.equal(last, xn - c + y)
     # uint8 HWC decoder pixels path == fp32 path
     u8 = ((c * 0.5 + 0.5) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
-    cf = u8.permute(0, 3, 1, 2).float().div(255).sub(0.5).mul(2.0)
+    cf = u8.permute(0, 3, 1, 2).float().div(255).sub(0.5).mul(2.0).contiguous()
     a = ops.ddrm_update(xn.cuda(), u8.cuda(), y.cuda(), t.cuda(), 0.2, z=z.cuda()).cpu()
     b = ops.ddrm_update(xn.cuda(), cf.cuda(), y.cuda(), t.cuda(), 0.2, z=z.cuda()).cpu()
     assert torch.equal(a, b)
@@ -195,6 +195,31 @@ def test_dct_freq_block_composite(ops, dtype, tol, fam, hw):
                  act=ops.ACT_SIGMOID, freq_mode=2, bs=f["bs"], low=f["low"], img_scale=boost.cuda(), mul=d, res=xd)
     out = nchw(ops.conv3x3(e, pack3(sd["p.conv_out.weight"], dtype), C, ops.IMPL_SIMT, bias=sd["p.conv_out.bias"].cuda()))
     assert rel(out, ref) < tol
+
+
+def test_mixed_dtype_stream_and_operands(ops):
+    """bf16 operands with an fp32 result stream: fp32 out + bf16 operand copy + fp32 residual; GroupNorm and the block
+    transform reading the fp32 stream and writing bf16 operands."""
+    B, Ci, Co, H, W = 2, 64, 128, 8, 8
+    x = bf16_round(torch.randn(B, Ci, H, W, generator=g(1)))
+    w = bf16_round(torch.randn(Co, Ci, 3, 3, generator=g(2)) / 24)
+    b = torch.randn(Co, generator=g(3))
+    res = torch.randn(B, Co, H, W, generator=g(4))          # fp32 residual, NOT rounded
+    ref = F.conv2d(x, w, b, padding=1) + res
+    out, out2 = ops.conv3x3(nhwc(x, torch.bfloat16), pack3(w, torch.bfloat16), Co, ops.IMPL_SIMT, out_dtype=torch.float32,
+                            out2_dtype=torch.bfloat16, bias=b.cuda(), res=nhwc(res))
+    assert out.dtype == torch.float32 and out2.dtype == torch.bfloat16
+    assert rel(nchw(out), ref) < 1e-5
+    assert torch.equal(out2, out.to(torch.bfloat16))
+    # GroupNorm: fp32 stream in, bf16 operand out + raw operand copy
+    xs = torch.randn(B, Ci, H, W, generator=g(5)) * 3 + 1
+    gamma, beta = torch.randn(Ci, generator=g(6)), torch.randn(Ci, generator=g(7))
+    st = ops.groupnorm_stats(nhwc(xs), 8)
+    y, raw = ops.groupnorm_apply(nhwc(xs), st, gamma.cuda(), beta.cuda(), ops.ACT_GELU, out_dtype=torch.bfloat16, raw_copy=True)
+    assert y.dtype == torch.bfloat16 and torch.equal(raw, nhwc(xs).to(torch.bfloat16))
+    assert rel(nchw(y), F.gelu(F.group_norm(xs, 8, gamma, beta, 1e-5))) < 4e-3
+    d = ops.block_transform(nhwc(xs), R.dct_matrix(4).cuda(), 0.0, 1.0, out_dtype=torch.bfloat16)
+    assert d.dtype == torch.bfloat16 and rel(nchw(d), R.block_transform(xs, R.dct_matrix(4))) < 4e-3
 
 
 @pytest.mark.parametrize("per_channel,bs,hw", [(0, 4, (10, 7)), (0, 8, (16, 16)), (1, 8, (8, 24)), (1, 8, (3, 5)), (0, 8, (1, 1))])

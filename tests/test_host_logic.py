@@ -1,0 +1,95 @@
+"""Host-side logic on the CPU: checkpoint layout, codec thread pool, sampler micro-batching, sharding (gloo, 2 ranks)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as R
+from oracle import weights as W
+
+
+@pytest.mark.parametrize("fam,cls,n", [("webp", "WebPDiffusionModel", 356), ("jpeg", "JPEGDiffusionModel", 356), ("avif", "AVIFDiffusionModel", 634)])
+def test_checkpoint_layout(fam, cls, n):
+    import ddpm_image_restoration_b200 as P
+    m = getattr(P, cls)()
+    sd = m.state_dict()
+    assert len(sd) == n
+    assert {k: tuple(v.shape) for k, v in sd.items()} == W.shapes(fam)
+    m.load_state_dict(W.make_state_dict(fam, 0))                      # raw state_dict, strict
+    wrapped = {"model_state_dict": W.make_state_dict(fam, 1), "epoch": 3}   # webp_training.py:796-804 layout
+    m.load_state_dict(wrapped["model_state_dict"])
+    assert sum(p.numel() for p in m.parameters()) == {"webp": 114398409, "jpeg": 114398409, "avif": 158284137}[fam]
+
+
+@pytest.mark.parametrize("codec,q", [("webp", 10), ("webp", 0), ("avif", 20), ("jpeg", 10), ("jpeg", 50), ("jpeg", 150)])
+def test_codec_pool_matches_oracle(codec, q):
+    from ddpm_image_restoration_b200 import codec as C
+    x = W.synthetic_images(5, 32, 48, seed=3)
+    fn = {"webp": C.webp_compress, "avif": C.avif_compress, "jpeg": C.jpeg_compress}[codec]
+    assert torch.equal(fn(x, q), R.codec_roundtrip(x, q, codec))
+    C.set_threads(2)
+    assert C.pool_threads() == 2
+    assert torch.equal(fn(x, q), R.codec_roundtrip(x, q, codec))
+    C.set_threads(C.host_threads())
+
+
+def test_codec_rejects_bad_input():
+    from ddpm_image_restoration_b200 import codec as C
+    with pytest.raises(ValueError):
+        C.webp_compress(torch.zeros(3, 8, 8), 10)
+    with pytest.raises(ValueError):
+        C.roundtrip_u8("gif", 10, np.zeros((1, 8, 8, 3), dtype=np.uint8))
+
+
+def test_sampler_micro_batching():
+    import ddpm_image_restoration_b200 as P
+    s = P.DDRMAVIFSampler(model=None)
+    assert s._chunks(64) == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    assert s._chunks(1) == [(0, 1)]
+    assert s._chunks(5) == [(0, 3), (3, 5)]
+    s.micro_batches = 3
+    ch = s._chunks(10)
+    assert ch[0][0] == 0 and ch[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+
+
+def test_shard_range():
+    from ddpm_image_restoration_b200.parallel import codec_threads_per_rank, shard_range
+    for n, world in ((512, 8), (10, 4), (3, 8), (64, 1)):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert codec_threads_per_rank(16, 8) == 2 and codec_threads_per_rank(4, 8) == 1
+
+
+def _rank_main(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from ddpm_image_restoration_b200.parallel import max_over_ranks, shard_range, sum_over_ranks
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(10, rank, world)
+    dist.barrier()
+    t = max_over_ranks(1.0 + rank)            # the slowest rank defines the step time
+    n = sum_over_ranks(hi - lo)               # units all ranks processed
+    q.put((rank, t, n, lo, hi))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_timing():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [2.0, 2.0]      # max over ranks
+    assert [r[2] for r in res] == [10.0, 10.0]    # every unit processed exactly once
+    assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 5, 5, 10)
