@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
     return ap.parse_args()
 
@@ -188,6 +189,9 @@ def main():
     host_cores = os.cpu_count() or 1
     codec.set_threads(max(1, host_cores // world))
 
+    if args.attn_expmode is not None:
+        from ddpm_image_restoration_b200 import _lib
+        _lib.lib().ddpmir_attention_set_expmode(args.attn_expmode)
     torch.manual_seed(0)
     model = {"avif": P.AVIFDiffusionModel, "webp": P.WebPDiffusionModel, "jpeg": P.JPEGDiffusionModel}[fam]()
     model = model.to(dev).eval().set_precision("bf16")

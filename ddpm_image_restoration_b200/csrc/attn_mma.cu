@@ -56,6 +56,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// truncating pack: keeps the high halves (1 PRMT on the ALU pipe instead of 1 F2FP).  Truncation biases every P
+// entry downward by < 2^-8 relative, but the row sums are taken from the SAME packed P (ones-column MMA), so the mean
+// bias cancels in O = (P V) / (P 1); what is left is rounding noise of the same order as round-to-nearest.
+__device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7632;\n" : "=r"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+    return r;
+}
+// exp2 for x <= 0 on the FMA/ALU pipes only (no MUFU, no F2I): Cody-Waite split with the 1.5*2^23 magic constant,
+// t = x + M holds n = rint(x) in its low mantissa bits, f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial
+// (max relative error 7.5e-5, far below the bf16 rounding of P), exponent add by integer arithmetic.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float M = 12582912.f;
+    const float t = x + M;
+    const float n = t - M;
+    const float f = x - n;
+    const float p = fmaf(fmaf(fmaf(0.05517166f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
     uint32_t y;
     asm("ex2.approx.ftz.bf16x2 %0, %1;\n" : "=r"(y) : "r"(x));
@@ -71,8 +91,13 @@ template <int CPR> __device__ __forceinline__ int swz(int row, int chunk) {
     return chunk ^ ((row / DIV) % MOD);
 }
 
-template <int HD, int MT, int NWARPS, int EXPMODE>
-__global__ void __launch_bounds__(NWARPS * 32)
+// EXPMODE: 0 = ex2.approx.f32 + cvt.rn pack, 1 = packed bf16x2 ex2, 2 = ex2.approx.f32 + truncating PRMT pack,
+//          3 / 4 = mode 2 with 2 / 3 of every 8 score tiles evaluated by ex2_poly (MUFU : FMA-pipe split 75:25 / 62:38)
+// SK = keys per pipeline stage (a multiple of the 64-key compute tile); 3-stage cp.async ring, ONE block barrier per
+// stage: at iteration t the barrier both publishes stage t and proves every warp is done with stage t-1, whose slot
+// is then refilled with stage t+2.
+template <int HD, int MT, int NWARPS, int EXPMODE, int SK, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
 attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, float scale_log2) {
     constexpr int CPR = HD / 8;            // 16-byte chunks per K/V row
     constexpr int NT = NWARPS * 32;
@@ -80,10 +105,12 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
     constexpr int NDT = HD / 8;            // 8-wide output column tiles
     constexpr int KSTEPS = HD >= 16 ? HD / 16 : 1;
     constexpr int TILE_ELEMS = KT * HD;
+    constexpr int STAGE_ELEMS = SK * HD;
+    constexpr int NSLOT = 3;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    bf16* Ks = reinterpret_cast<bf16*>(smem_raw);              // [2][KT][HD]
-    bf16* Vs = Ks + 2 * TILE_ELEMS;                            // [2][KT][HD]
+    bf16* Ks = reinterpret_cast<bf16*>(smem_raw);              // [3][SK][HD]
+    bf16* Vs = Ks + NSLOT * STAGE_ELEMS;                       // [3][SK][HD]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z, h = blockIdx.y;
@@ -92,16 +119,23 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
     const bf16* kbase = qbase + C;
     const bf16* vbase = qbase + 2 * C;
 
-    auto load_tile = [&](int t, int stage) {
-        const int k0 = t * KT;
-        bf16* kd = Ks + stage * TILE_ELEMS;
-        bf16* vd = Vs + stage * TILE_ELEMS;
-        for (int i = tid; i < KT * CPR; i += NT) {
-            const int row = i / CPR, ch = i - row * CPR;
-            const long long g = (long long)(k0 + row) * rstride + ch * 8;
-            const int so = row * HD + swz<CPR>(row, ch) * 8;
-            cp_async16(kd + so, kbase + g);
-            cp_async16(vd + so, vbase + g);
+    // per-thread copy plan of one stage: SK*CPR 16-byte chunks of K and as many of V, CH chunk pairs per thread
+    constexpr int CH = (SK * CPR + NT - 1) / NT;
+    auto load_stage = [&](int t, int slot) {
+        const bf16* ksrc = kbase + (long long)t * SK * rstride;
+        const bf16* vsrc = vbase + (long long)t * SK * rstride;
+        bf16* kd = Ks + slot * STAGE_ELEMS;
+        bf16* vd = Vs + slot * STAGE_ELEMS;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int i = tid + c * NT;
+            if (SK * CPR % NT == 0 || i < SK * CPR) {
+                const int row = i / CPR, ch = i % CPR;
+                const long long g = (long long)row * rstride + ch * 8;
+                const int so = row * HD + swz<CPR>(row, ch) * 8;
+                cp_async16(kd + so, ksrc + g);
+                cp_async16(vd + so, vsrc + g);
+            }
         }
     };
 
@@ -142,25 +176,27 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
     }
     const uint32_t ones = (lane >> 2) == 0 ? 0x3F803F80u : 0u;  // B fragment of a ones column at n = 0
 
-    const int ntiles = L / KT;
-    load_tile(0, 0);
+    const int nstages = L / SK;
+    load_stage(0, 0);
     cp_async_commit();
+    if (nstages > 1) { load_stage(1, 1); cp_async_commit(); }
 
     const uint32_t ks_s = (uint32_t)__cvta_generic_to_shared(Ks);
     const uint32_t vs_s = (uint32_t)__cvta_generic_to_shared(Vs);
     const int lrow = lane & 7, lmat = lane >> 3;
 
-    for (int t = 0; t < ntiles; ++t) {
-        if (t + 1 < ntiles) {
-            load_tile(t + 1, (t + 1) & 1);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+    int slot = 0;
+    for (int t = 0; t < nstages; ++t) {
+        if (t + 1 < nstages) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
-        const uint32_t kst = ks_s + (t & 1) * TILE_ELEMS * 2;
-        const uint32_t vst = vs_s + (t & 1) * TILE_ELEMS * 2;
+        if (t + 2 < nstages) {
+            load_stage(t + 2, slot >= 1 ? slot - 1 : NSLOT - 1);   // slot of stage t-1 == slot of stage t+2
+            cp_async_commit();
+        }
+#pragma unroll 1
+      for (int sub = 0; sub < SK / KT; ++sub) {
+        const uint32_t kst = ks_s + (slot * STAGE_ELEMS + sub * TILE_ELEMS) * 2;
+        const uint32_t vst = vs_s + (slot * STAGE_ELEMS + sub * TILE_ELEMS) * 2;
 
         // ---- S = Q K^T ----------------------------------------------------------------------------------
         float s[MT][8][4];
@@ -230,6 +266,18 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
                 if (EXPMODE == 1) {
                     p01 = ex2_bf16x2(pack_bf16(x0, x1));
                     p23 = ex2_bf16x2(pack_bf16(x2, x3));
+                } else if (EXPMODE == 2) {
+                    p01 = pack_bf16_trunc(ex2f(x0), ex2f(x1));
+                    p23 = pack_bf16_trunc(ex2f(x2), ex2f(x3));
+                } else if (EXPMODE == 3 || EXPMODE == 4) {
+                    const bool poly = (EXPMODE == 3) ? ((nt & 3) == 3) : (nt == 2 || nt == 5 || nt == 7);
+                    if (poly) {
+                        p01 = pack_bf16_trunc(ex2_poly(x0), ex2_poly(x1));
+                        p23 = pack_bf16_trunc(ex2_poly(x2), ex2_poly(x3));
+                    } else {
+                        p01 = pack_bf16_trunc(ex2f(x0), ex2f(x1));
+                        p23 = pack_bf16_trunc(ex2f(x2), ex2f(x3));
+                    }
                 } else {
                     p01 = pack_bf16(ex2f(x0), ex2f(x1));
                     p23 = pack_bf16(ex2f(x2), ex2f(x3));
@@ -265,7 +313,8 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
                 for (int mt = 0; mt < MT; ++mt) mma_16816(o[mt][0], pf[mt][kk], vf[0], vf[1]);
             }
         }
-        __syncthreads();
+      }
+        slot = slot + 1 == NSLOT ? 0 : slot + 1;
     }
 
     // ---- normalise and store --------------------------------------------------------------------------------
@@ -285,11 +334,11 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
     }
 }
 
-template <int HD, int MT, int NWARPS, int EXPMODE>
-int launch(const void* qkv, void* out, int B, int L, int C, int heads, cudaStream_t st) {
+template <int HD, int MT, int NWARPS, int EXPMODE, int SK, int MINB>
+int launch_sk(const void* qkv, void* out, int B, int L, int C, int heads, cudaStream_t st) {
     constexpr int ROWS = NWARPS * MT * 16;
-    const size_t smem = (size_t)4 * KT * HD * sizeof(bf16);
-    auto kern = attn_mma_kernel<HD, MT, NWARPS, EXPMODE>;
+    const size_t smem = (size_t)3 * 2 * SK * HD * sizeof(bf16);
+    auto kern = attn_mma_kernel<HD, MT, NWARPS, EXPMODE, SK, MINB>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { ddpmir_set_error("attention: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
@@ -301,13 +350,26 @@ int launch(const void* qkv, void* out, int B, int L, int C, int heads, cudaStrea
     return DDPMIR_OK;
 }
 
+// stage size: as many keys as fit the budget and divide L (fewer block barriers per key), 64 otherwise
+template <int HD, int MT, int NWARPS, int EXPMODE>
+int launch(const void* qkv, void* out, int B, int L, int C, int heads, cudaStream_t st) {
+    constexpr int SKMAX = HD <= 16 ? 256 : (HD == 32 ? 128 : 64);
+    constexpr int MINB = (HD <= 16 && MT == 1) ? 4 : 1;
+    if (SKMAX > 64 && L % SKMAX == 0) return launch_sk<HD, MT, NWARPS, EXPMODE, SKMAX, MINB>(qkv, out, B, L, C, heads, st);
+    return launch_sk<HD, MT, NWARPS, EXPMODE, 64, MINB>(qkv, out, B, L, C, heads, st);
+}
+
 int g_expmode = 0;
+int g_mt = 1;
 
 }  // namespace
 
-// test / tuning hook: 0 = fp32 ex2 per score, 1 = packed bf16x2 ex2
+// test / tuning hook: expmode 0 = fp32 ex2 + cvt pack, 1 = packed bf16x2 ex2, 2 = fp32 ex2 + truncating pack;
+// +16 selects two 16-row tiles per warp (head_dim 8/16 only)
 extern "C" int ddpmir_attention_set_expmode(int mode) {
-    g_expmode = mode ? 1 : 0;
+    g_expmode = mode & 15;
+    if (g_expmode > 4) g_expmode = 0;
+    g_mt = (mode & 16) ? 2 : 1;
     return DDPMIR_OK;
 }
 
@@ -316,10 +378,13 @@ int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int h
 int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, cudaStream_t st) {
     const int hd = C / heads;
     if (L % KT != 0) return DDPMIR_ERR_UNSUPPORTED;
-#define GO(HD, MT, NW) (g_expmode ? launch<HD, MT, NW, 1>(qkv, out, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, B, L, C, heads, st))
+#define GO(HD, MT, NW) (g_expmode == 1 ? launch<HD, MT, NW, 1>(qkv, out, B, L, C, heads, st) : \
+                        g_expmode == 2 ? launch<HD, MT, NW, 2>(qkv, out, B, L, C, heads, st) : \
+                        g_expmode == 3 ? launch<HD, MT, NW, 3>(qkv, out, B, L, C, heads, st) : \
+                        g_expmode == 4 ? launch<HD, MT, NW, 4>(qkv, out, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, B, L, C, heads, st))
     switch (hd) {
-        case 8: return GO(8, 1, 8);
-        case 16: return GO(16, 1, 8);
+        case 8: return g_mt == 2 ? GO(8, 2, 8) : GO(8, 1, 8);
+        case 16: return g_mt == 2 ? GO(16, 2, 8) : GO(16, 1, 8);
         case 32: return GO(32, 1, 8);
         case 64: return GO(64, 1, 4);
         case 128: return GO(128, 1, 4);

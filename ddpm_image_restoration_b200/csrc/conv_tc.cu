@@ -21,7 +21,6 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
 
@@ -116,8 +115,8 @@ struct TcParams {
     int taps;
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void* __restrict__ out,
                 EpiDev ep, TcParams p) {
     constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -201,10 +200,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
             if (m_ok) {
+                const int n = n0 + c0;
+                if (n + 16 <= p.N && (p.N & 15) == 0) {
+                    epi_chunk16(ep, row, v, m, n, out);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.N) epi_store(ep, out, m, n, epi_apply(ep, row, v[j], m, n));
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < p.N) epi_store(ep, out, m, n + j, epi_apply(ep, row, v[j], m, n + j));
                 }
             }
         }
@@ -235,17 +237,17 @@ EncodeTiledFn get_encode() {
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev& ep, const TcParams& p, cudaStream_t st) {
     constexpr int smem = STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { ddpmir_set_error("igemm_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
         attr_set = true;
     }
     dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BLOCK_N));
-    igemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, smem, st>>>(ta, tb, out, ep, p);
+    igemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, out, ep, p);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -291,5 +293,10 @@ int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const
         if (r != CUDA_SUCCESS) { ddpmir_set_error("igemm_tc: weight tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
     }
     EpiDev ep = make_epi(epi, H, W, N, DDPMIR_BF16);
-    return block_n == 128 ? launch<128>(ta, tb, out, ep, p, st) : launch<64>(ta, tb, out, ep, p, st);
+    // short K loops (1x1 convolutions with K <= 128) are bandwidth-bound: a 2-stage ring keeps the CTA small so that
+    // 3-4 CTAs share an SM and one CTA's epilogue overlaps the others' loads; long K loops get a 4-stage ring
+    const int num_kb = taps * (Cin / BLOCK_K);
+    if (num_kb <= 2)
+        return block_n == 128 ? launch<128, 2>(ta, tb, out, ep, p, st) : launch<64, 2>(ta, tb, out, ep, p, st);
+    return block_n == 128 ? launch<128, 4>(ta, tb, out, ep, p, st) : launch<64, 4>(ta, tb, out, ep, p, st);
 }

@@ -100,3 +100,102 @@ __device__ __forceinline__ void epi_store(const EpiDev& p, void* out, long long 
     st_any(out, p.out_dtype, m * p.N + n, v);
     if (p.out2) st_any(p.out2, p.out2_dtype, m * p.N + n, v);
 }
+
+// ---- vectorised epilogue over 16 consecutive output channels of one row (tcgen05 kernel: one TMEM lane = one row) ----
+__device__ __forceinline__ void ld16_f32(const float* p, float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 a = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+    }
+}
+__device__ __forceinline__ void ld16_any(const void* base, int dtype, long long idx, float (&v)[16]) {
+    if (dtype == DDPMIR_F32) {
+        ld16_f32(reinterpret_cast<const float*>(base) + idx, v);
+    } else {
+        const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + idx);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint4 r = p[i];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h[k]);
+                v[8 * i + 2 * k] = f.x; v[8 * i + 2 * k + 1] = f.y;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void st16_any(void* base, int dtype, long long idx, const float (&v)[16]) {
+    if (dtype == DDPMIR_F32) {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + idx);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint4 r;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
+            p[i] = r;
+        }
+    }
+}
+
+// v[16] = accumulators of row m, channels n .. n+15 (n % 16 == 0, n + 16 <= N, N % 16 == 0)
+__device__ __forceinline__ void epi_chunk16(const EpiDev& p, const EpiRow& r, float (&v)[16], long long m, int n, void* out) {
+    float t[16];
+    const float* bias = (p.freq_mode == 2 && !r.low) ? p.bias2 : p.bias;
+    if (bias) {
+        ld16_f32(bias + n, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += t[j];
+    }
+    if (p.row_bias) {
+        ld16_f32(p.row_bias + (long long)r.b * p.N + n, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += t[j];
+    }
+    switch (p.act) {
+        case DDPMIR_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+        case DDPMIR_ACT_LRELU02:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+            break;
+        case DDPMIR_ACT_SIGMOID:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+            break;
+        case DDPMIR_ACT_NONE:
+            break;
+        default:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_apply(p.act, v[j]);
+    }
+    if (p.freq_mode == 1 && ((n < (p.N >> 1)) != r.low)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+    if (r.scale != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= r.scale;
+    }
+    const long long idx = m * p.N + n;
+    if (p.mul) {
+        ld16_any(p.mul, p.mul_dtype, idx, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= t[j];
+    }
+    if (p.res) {
+        ld16_any(p.res, p.res_dtype, idx, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += t[j];
+    }
+    st16_any(out, p.out_dtype, idx, v);
+    if (p.out2) st16_any(p.out2, p.out2_dtype, idx, v);
+}

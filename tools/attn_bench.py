@@ -1,0 +1,27 @@
+"""Times ddpmir_attention alone (tuning aid):  python tools/attn_bench.py [hd] [heads] [L] [B] [expmode]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ddpm_image_restoration_b200 import ops, _lib
+
+hd = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+heads = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+L = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+B = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+if len(sys.argv) > 5:
+    _lib.lib().ddpmir_attention_set_expmode(int(sys.argv[5]))
+C = hd * heads
+qkv = (torch.randn(B, L, 3 * C, device="cuda") * 1.0).to(torch.bfloat16)
+for _ in range(2):
+    out = ops.attention(qkv, heads)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 3
+e0.record()
+for _ in range(n):
+    out = ops.attention(qkv, heads)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+scores = B * heads * L * L
+print(f"attention hd={hd} heads={heads} L={L} B={B}: {ms:.3f} ms  {scores / ms / 1e9:.3f} Tscores/s  "
+      f"{scores / (ms * 1e-3) / 148 / 1.965e9:.2f} scores/clk/SM@1965MHz  {4.0 * scores * hd / ms / 1e9:.1f} TFLOP/s")
