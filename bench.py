@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
+    ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
     return ap.parse_args()
 
@@ -237,6 +238,26 @@ def main():
         attn = ops.timing_end().get("attention", [])
         return ms, wall, dict(launches=ops.LAUNCHES[0], h2d=st["h2d"], d2h=st["d2h"], codec_s=st["codec_s"], attn=attn,
                               finite=bool(torch.isfinite(st["x_t"]).all()))
+
+    if args.profile_ops and rank == 0:
+        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches)
+        st = sampler.begin(y_host.to(dev), q, steps=traj)
+        for i in (traj - 1, traj - 2):
+            sampler.step(st, i)
+        torch.cuda.synchronize()
+        ops.timing_begin(lambda name, tag: True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); sampler.step(st, traj - 3); e1.record()
+        torch.cuda.synchronize()
+        agg = {}
+        for name, lst in ops.timing_end().items():
+            for ms, tag in lst:
+                k = (name, tag)
+                a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += ms
+        tot = sum(v[1] for v in agg.values())
+        print(f"# per-op CUDA-event times of one sampler step ({e0.elapsed_time(e1):.1f} ms total, {tot:.1f} ms in GEMM/conv/attention)", file=sys.stderr)
+        for (name, tag), (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            print(f"#   {ms:9.3f} ms  x{n:3d}  {name:10s} {tag}", file=sys.stderr)
 
     clocks = ClockSampler(local)
     clocks.start()

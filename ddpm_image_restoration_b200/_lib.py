@@ -39,6 +39,9 @@ _SIGNATURES = {
     "ddpmir_phase_consistency": (c_int, [_P, _P, c_float, c_int, c_int, c_int, _P, _P, _P]),
     "ddpmir_svd_lowrank": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),
     "ddpmir_color_l1": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_mse": (c_int, [_P, _P, c_int64, _P, _P, _P]),
+    "ddpmir_ssim": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_freq_loss_terms": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ddpmir_time_embed": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "ddpmir_linear_rows": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "ddpmir_groupnorm_stats": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
@@ -57,7 +60,7 @@ _SIGNATURES = {
 }
 
 # not part of the public header: tuning hook used by tests/bench
-_PRIVATE = {"ddpmir_attention_set_expmode": (c_int, [c_int])}
+_PRIVATE = {"ddpmir_attention_set_expmode": (c_int, [c_int]), "ddpmir_igemm_set_variant": (c_int, [c_int])}
 
 _lib = None
 

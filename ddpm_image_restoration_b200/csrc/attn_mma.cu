@@ -251,13 +251,17 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
             const float mn0 = fmaxf(mrow[mt][0], mx0 * scale_log2);
             const float mn1 = fmaxf(mrow[mt][1], mx1 * scale_log2);
-            const float c0 = ex2f(mrow[mt][0] - mn0), c1 = ex2f(mrow[mt][1] - mn1);
-            mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+            // rescale the running output / row sums only when some row of this warp saw a new maximum (after the first
+            // few key tiles that is rare: the expected number of record maxima over n tiles is ~ln n)
+            if (__any_sync(0xffffffffu, mn0 != mrow[mt][0] || mn1 != mrow[mt][1])) {
+                const float c0 = ex2f(mrow[mt][0] - mn0), c1 = ex2f(mrow[mt][1] - mn1);
+                mrow[mt][0] = mn0; mrow[mt][1] = mn1;
 #pragma unroll
-            for (int dt = 0; dt < NDT; ++dt) {
-                o[mt][dt][0] *= c0; o[mt][dt][1] *= c0; o[mt][dt][2] *= c1; o[mt][dt][3] *= c1;
+                for (int dt = 0; dt < NDT; ++dt) {
+                    o[mt][dt][0] *= c0; o[mt][dt][1] *= c0; o[mt][dt][2] *= c1; o[mt][dt][3] *= c1;
+                }
+                ls[mt][0] *= c0; ls[mt][1] *= c0; ls[mt][2] *= c1; ls[mt][3] *= c1;
             }
-            ls[mt][0] *= c0; ls[mt][1] *= c0; ls[mt][2] *= c1; ls[mt][3] *= c1;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 const float x0 = fmaf(s[mt][nt][0], scale_log2, -mn0), x1 = fmaf(s[mt][nt][1], scale_log2, -mn0);
@@ -359,7 +363,7 @@ int launch(const void* qkv, void* out, int B, int L, int C, int heads, cudaStrea
     return launch_sk<HD, MT, NWARPS, EXPMODE, 64, MINB>(qkv, out, B, L, C, heads, st);
 }
 
-int g_expmode = 0;
+int g_expmode = -1;   // -1 = auto: mode 3 (25 % of the exps on the FMA pipe) at head_dim 8, mode 0 otherwise (measured on B200)
 int g_mt = 1;
 
 }  // namespace
@@ -367,6 +371,7 @@ int g_mt = 1;
 // test / tuning hook: expmode 0 = fp32 ex2 + cvt pack, 1 = packed bf16x2 ex2, 2 = fp32 ex2 + truncating pack;
 // +16 selects two 16-row tiles per warp (head_dim 8/16 only)
 extern "C" int ddpmir_attention_set_expmode(int mode) {
+    if (mode < 0) { g_expmode = -1; g_mt = 1; return DDPMIR_OK; }
     g_expmode = mode & 15;
     if (g_expmode > 4) g_expmode = 0;
     g_mt = (mode & 16) ? 2 : 1;
@@ -378,10 +383,11 @@ int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int h
 int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, cudaStream_t st) {
     const int hd = C / heads;
     if (L % KT != 0) return DDPMIR_ERR_UNSUPPORTED;
-#define GO(HD, MT, NW) (g_expmode == 1 ? launch<HD, MT, NW, 1>(qkv, out, B, L, C, heads, st) : \
-                        g_expmode == 2 ? launch<HD, MT, NW, 2>(qkv, out, B, L, C, heads, st) : \
-                        g_expmode == 3 ? launch<HD, MT, NW, 3>(qkv, out, B, L, C, heads, st) : \
-                        g_expmode == 4 ? launch<HD, MT, NW, 4>(qkv, out, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, B, L, C, heads, st))
+    const int em = g_expmode >= 0 ? g_expmode : (hd == 8 ? 3 : 0);
+#define GO(HD, MT, NW) (em == 1 ? launch<HD, MT, NW, 1>(qkv, out, B, L, C, heads, st) : \
+                        em == 2 ? launch<HD, MT, NW, 2>(qkv, out, B, L, C, heads, st) : \
+                        em == 3 ? launch<HD, MT, NW, 3>(qkv, out, B, L, C, heads, st) : \
+                        em == 4 ? launch<HD, MT, NW, 4>(qkv, out, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, B, L, C, heads, st))
     switch (hd) {
         case 8: return g_mt == 2 ? GO(8, 2, 8) : GO(8, 1, 8);
         case 16: return g_mt == 2 ? GO(16, 2, 8) : GO(16, 1, 8);

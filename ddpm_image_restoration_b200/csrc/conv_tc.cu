@@ -216,6 +216,129 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
 }
 
+// ---- persistent, weight-resident variant -------------------------------------------------------------------
+// For the full-resolution layers (M = B*H*W is huge, N*K small) the whole weight matrix fits in shared memory.  One
+// CTA per SM loads it ONCE, then streams activation boxes through a deep TMA ring while looping over its pixel tiles;
+// the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct StreamParams {
+    TcParams t;
+    int num_tiles;     // M tiles of 128 pixels
+    int nb;            // weight rows per k-block tile in smem (N rounded up to 8)
+    int a_stages;      // depth of the activation ring
+};
+
+template <int TCOLS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+igemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       void* __restrict__ out, EpiDev ep, StreamParams sp) {
+    const TcParams& p = sp.t;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int kc = p.Cin / BLOCK_K;
+    const int num_kb = p.taps * kc;
+    const int w_tile_bytes = sp.nb * BLOCK_K * 2;
+    unsigned char* sw = smem;                                    // num_kb weight tiles
+    unsigned char* sa = smem + num_kb * w_tile_bytes;             // a_stages x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sa + sp.a_stages * A_STAGE_BYTES);
+    uint64_t* w_full = bars;
+    uint64_t* full = bars + 1;
+    uint64_t* empty = full + sp.a_stages;
+    uint64_t* acc_full = empty + sp.a_stages;    // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        mbar_init(w_full, 1);
+        for (int s = 0; s < sp.a_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)(num_kb * w_tile_bytes));
+            for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sw + kb * w_tile_bytes, &tmap_b, w_full, kb * BLOCK_K, 0);
+            const int hw = p.H * p.W;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < sp.num_tiles; tile += gridDim.x) {
+                const long long m0 = (long long)tile * BLOCK_M;
+                const int b0 = (int)(m0 / hw);
+                const int rem = (int)(m0 - (long long)b0 * hw);
+                const int h0 = rem / p.W, w0 = rem - h0 * p.W;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % sp.a_stages, ph = (it / sp.a_stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int tap = kb / kc, c0 = (kb - tap * kc) * BLOCK_K;
+                    const int dh = p.taps == 9 ? tap / 3 - 1 : 0, dw = p.taps == 9 ? tap % 3 - 1 : 0;
+                    mbar_expect_tx(&full[s], A_STAGE_BYTES);
+                    tma_load_4d(sa + s * A_STAGE_BYTES, &tmap_a, &full[s], c0, w0 + dw, h0 + dh, b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            mbar_wait(w_full, 0);
+            int it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < sp.num_tiles; tile += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * (TCOLS / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % sp.a_stages, ph = (it / sp.a_stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sa + s * A_STAGE_BYTES), b_addr = smem_u32(sw + kb * w_tile_bytes);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int lane_base = 32 * (warp & 3);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < sp.num_tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            mbar_wait(&acc_full[buf], (i >> 1) & 1);
+            tc_fence_after();
+            const long long m = (long long)tile * BLOCK_M + lane_base + lane;
+            const bool m_ok = m < p.M;
+            EpiRow row;
+            if (m_ok) row = epi_row(ep, m);
+            const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * (TCOLS / 2));
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.N; c0 += 16) {
+                float v[16];
+                tmem_ld16(t_addr + (uint32_t)c0, v);
+                if (m_ok) epi_chunk16(ep, row, v, m, c0, out);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -252,7 +375,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev
     return DDPMIR_OK;
 }
 
+template <int TCOLS>
+int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev& ep, const StreamParams& sp, int smem,
+                  int grid, cudaStream_t st) {
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_tc_stream_kernel<TCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { ddpmir_set_error("igemm_tc_stream: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
+        attr_smem = smem;
+    }
+    igemm_tc_stream_kernel<TCOLS><<<grid, NUM_THREADS, smem, st>>>(ta, tb, out, ep, sp);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+int g_num_sms = 0;
+int g_tc_variant = 0;   // 0 = auto, 1 = tiled kernel only, 2 = streaming kernel whenever legal
+
 }  // namespace
+
+extern "C" int ddpmir_igemm_set_variant(int v) { g_tc_variant = v; return DDPMIR_OK; }
 
 int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const void* w, int N,
                     const ddpmir_epilogue_t* epi, void* out, cudaStream_t st) {
@@ -280,7 +422,40 @@ int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { ddpmir_set_error("igemm_tc: activation tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
     }
-    const int block_n = (N % 128 == 0) ? 128 : 64;
+    // persistent weight-resident kernel: whole [N, K] weight in shared memory, >= 2 tiles per SM
+    const long long w_bytes = (long long)N * taps * Cin * 2;
+    const int num_tiles = ceil_div(p.M, BLOCK_M);
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const bool stream_ok = N % 16 == 0 && N <= 256 && w_bytes <= 112 * 1024;
+    if (g_tc_variant != 1 && stream_ok && (g_tc_variant == 2 || num_tiles >= 2 * g_num_sms)) {
+        const cuuint64_t K = (cuuint64_t)taps * Cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)N};
+        cuuint64_t strides[1] = {K * 2};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)N};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ddpmir_set_error("igemm_tc: weight tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
+        StreamParams sp;
+        sp.t = p; sp.num_tiles = num_tiles; sp.nb = N;
+        const int budget = 220 * 1024 - (int)w_bytes - 1024 - 256;
+        sp.a_stages = budget / A_STAGE_BYTES;
+        if (sp.a_stages > 8) sp.a_stages = 8;
+        const int smem = (int)w_bytes + sp.a_stages * A_STAGE_BYTES + (2 * sp.a_stages + 5) * 8 + 16 + 1024;
+        const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+        EpiDev ep = make_epi(epi, H, W, N, DDPMIR_BF16);
+        if (N <= 64) return launch_stream<128>(ta, tb, out, ep, sp, smem, grid, st);
+        if (N <= 128) return launch_stream<256>(ta, tb, out, ep, sp, smem, grid, st);
+        return launch_stream<512>(ta, tb, out, ep, sp, smem, grid, st);
+    }
+    // widest N tile that divides N: per k-block a CTA moves (128 + BLOCK_N) x 128 B for 128 x BLOCK_N x 64 MACs, and the
+    // L2->SM path (~42 B/clk/SM) is what bounds the tensor pipe, so wider is better
+    const int block_n = (N % 256 == 0 && taps * (Cin / BLOCK_K) > 2) ? 256 : (N % 128 == 0) ? 128 : 64;
     {
         const cuuint64_t K = (cuuint64_t)taps * Cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)N};
@@ -298,5 +473,6 @@ int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const
     const int num_kb = taps * (Cin / BLOCK_K);
     if (num_kb <= 2)
         return block_n == 128 ? launch<128, 2>(ta, tb, out, ep, p, st) : launch<64, 2>(ta, tb, out, ep, p, st);
+    if (block_n == 256) return launch<256, 4>(ta, tb, out, ep, p, st);
     return block_n == 128 ? launch<128, 4>(ta, tb, out, ep, p, st) : launch<64, 4>(ta, tb, out, ep, p, st);
 }

@@ -111,6 +111,61 @@ row_ifft_blend_kernel(const float2* __restrict__ ws, const float* __restrict__ x
         out[r0 * W + i] = alpha * x[r0 * W + i] + beta * (a[i].x * inv_n);
 }
 
+// frequency terms of frequency_aware_loss (webp_training.py:114-126): column FFT of the row-transformed pred and
+// target planes over the rfft2 half spectrum (columns 0..W/2), accumulating sum (|P|-|T|)^2 and
+// sum (angle P - angle T)^2.  The row pass transformed x*0.5+0.5 (see row_fft_affine_kernel).
+__global__ void __launch_bounds__(FFT_THREADS)
+col_loss_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, int H, int W, int cols_per_cta,
+                double* __restrict__ acc) {
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + FFT_ELEMS;
+    const int p = blockIdx.y;
+    const int half = W / 2 + 1;
+    const int c0 = blockIdx.x * cols_per_cta;
+    const int nb = min(cols_per_cta, half - c0);     // columns of pred; the same columns of target follow
+    const float2* pp = wp + (long long)p * H * W;
+    const float2* tp = wt + (long long)p * H * W;
+    for (int i = threadIdx.x; i < nb * H; i += FFT_THREADS) {
+        const int h = i / nb, c = i - h * nb;
+        a[c * H + h] = pp[(long long)h * W + c0 + c];
+        a[(nb + c) * H + h] = tp[(long long)h * W + c0 + c];
+    }
+    __syncthreads();
+    fft_batch(a, b, 2 * nb, H, -1.f);
+    float sm2 = 0.f, sp2 = 0.f;
+    for (int i = threadIdx.x; i < nb * H; i += FFT_THREADS) {
+        const float2 P = a[i], T = a[nb * H + i];
+        const float dm = sqrtf(P.x * P.x + P.y * P.y) - sqrtf(T.x * T.x + T.y * T.y);
+        const float dp = atan2f(P.y, P.x) - atan2f(T.y, T.x);
+        sm2 = fmaf(dm, dm, sm2); sp2 = fmaf(dp, dp, sp2);
+    }
+    sm2 = warp_sum(sm2); sp2 = warp_sum(sp2);
+    __shared__ float red[2][FFT_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wid] = sm2; red[1][wid] = sp2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0;
+        for (int w = 0; w < FFT_THREADS / 32; ++w) v += (double)red[threadIdx.x][w];
+        atomicAdd(&acc[threadIdx.x], v);
+    }
+}
+
+// forward row FFT of x*0.5+0.5 (the [0,1] images of webp_training.py:111-112)
+__global__ void __launch_bounds__(FFT_THREADS)
+row_fft_affine_kernel(const float* __restrict__ x, float2* __restrict__ ws, long long rows_total, int W, int rows_per_cta) {
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + FFT_ELEMS;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const int nb = (int)min((long long)rows_per_cta, rows_total - r0);
+    for (int i = threadIdx.x; i < nb * W; i += FFT_THREADS) a[i] = make_float2(__fadd_rn(__fmul_rn(x[r0 * W + i], 0.5f), 0.5f), 0.f);
+    __syncthreads();
+    fft_batch(a, b, nb, W, -1.f);
+    for (int i = threadIdx.x; i < nb * W; i += FFT_THREADS) ws[r0 * W + i] = a[i];
+}
+
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int setup_smem() {
@@ -121,6 +176,8 @@ int setup_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(col_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(row_ifft_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(col_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(row_fft_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { ddpmir_set_error("fft: shared-memory opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
     done = true;
     return DDPMIR_OK;
@@ -170,6 +227,28 @@ extern "C" int ddpmir_phase_consistency(const float* x, const float* phasor, flo
     DDPMIR_LAUNCH_CHECK();
     row_ifft_blend_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws, x, out, rows, W, rpc, alpha,
                                                                                 1.f / ((float)H * (float)W));
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+extern "C" int ddpmir_freq_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
+                                      float* ws_target, double* acc2, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(pred && target && ws_pred && ws_target && acc2, "freq_loss_terms: null pointer");
+    int rc = check_shape(planes, H, W);
+    if (rc) return rc;
+    if ((rc = setup_smem())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(acc2, 0, 2 * sizeof(double), st);
+    const long long rows = (long long)planes * H;
+    const int rpc = FFT_ELEMS / W;
+    int cpc = FFT_ELEMS / H / 2;      // pred + target columns share one shared-memory batch
+    if (cpc > 8) cpc = 8;
+    if (cpc < 1) { ddpmir_set_error("freq_loss_terms: H too large"); return DDPMIR_ERR_UNSUPPORTED; }
+    row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(pred, (float2*)ws_pred, rows, W, rpc);
+    row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(target, (float2*)ws_target, rows, W, rpc);
+    DDPMIR_LAUNCH_CHECK();
+    col_loss_kernel<<<dim3(ceil_div(W / 2 + 1, cpc), planes), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_pred, (const float2*)ws_target,
+                                                                                          H, W, cpc, acc2);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

@@ -183,6 +183,37 @@ def color_l1(pred, target):
     return out[0]
 
 
+def mse(a, b):
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    ws = torch.empty((1,), dtype=torch.float64, device=a.device)
+    _lib.check(_lib.lib().ddpmir_mse(_p(_f32(a, "a")), _p(_f32(b, "b")), a.numel(), _p(out), _p(ws), _stream()), "mse")
+    LAUNCHES[0] += 2
+    return out[0]
+
+
+def ssim(x, y, clamp01=False):
+    """SSIM of the [0,1] images x*0.5+0.5, y*0.5+0.5 (pytorch_msssim.ssim semantics), x, y [B,C,H,W] in [-1,1]."""
+    B, C, H, W = x.shape
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((1,), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.lib().ddpmir_ssim(_p(_f32(x, "x")), _p(_f32(y, "y")), B * C, H, W, int(clamp01), _p(out), _p(ws), _stream()),
+               "ssim")
+    LAUNCHES[0] += 2
+    return out[0]
+
+
+def freq_loss_terms(pred, target):
+    """Returns a float64 tensor [2]: sum of squared rfft2-magnitude differences and of squared phase differences."""
+    B, C, H, W = pred.shape
+    wp = torch.empty((B * C, H, W, 2), dtype=torch.float32, device=pred.device)
+    wt = torch.empty_like(wp)
+    acc = torch.empty((2,), dtype=torch.float64, device=pred.device)
+    _lib.check(_lib.lib().ddpmir_freq_loss_terms(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B * C, H, W, _p(wp), _p(wt),
+                                                 _p(acc), _stream()), "freq_loss_terms")
+    LAUNCHES[0] += 3
+    return acc
+
+
 # ---------------------------------------------------------------------------------------------------------
 # UNet-level (NHWC activations)
 # ---------------------------------------------------------------------------------------------------------

@@ -120,6 +120,23 @@ int ddpmir_svd_lowrank(const float* x, int planes, int H, int W, int k, float* o
 int ddpmir_color_l1(const float* pred, const float* target, int B, int H, int W, float* out_scalar, double* ws,
                     ddpmir_stream_t stream);
 
+/* Forward values of the remaining loss terms (no gradients yet: the training step's backward kernels are a later
+ * round).  ddpmir_mse: F.mse_loss(a, b), webp_training.py:108.  ws: 1 double. */
+int ddpmir_mse(const float* a, const float* b, int64_t n, float* out_scalar, double* ws, ddpmir_stream_t stream);
+
+/* pytorch_msssim.ssim(x*0.5+0.5, y*0.5+0.5, data_range=1.0, size_average=True) (gaussian window 11, sigma 1.5,
+ * 'valid' separable filtering, K=(0.01,0.03)); clamp01 != 0 clamps the [0,1] images first (0409_method.ipynb#c0:L67-68,79;
+ * webp_training.py:111-112,129 does not clamp).  x, y: [planes, H, W] fp32 in [-1,1].  ws: 1 double.
+ * PARITY UNPINNED: the third-party package is not installed and the reference pins no version. */
+int ddpmir_ssim(const float* x, const float* y, int planes, int H, int W, int clamp01, float* out_scalar, double* ws,
+                ddpmir_stream_t stream);
+
+/* Frequency terms of frequency_aware_loss, webp_training.py:114-126, over all planes at once:
+ * acc2[0] = sum (|rfft2 P| - |rfft2 T|)^2, acc2[1] = sum (angle rfft2 P - angle rfft2 T)^2 with P = pred*0.5+0.5,
+ * T = target*0.5+0.5 (H, W powers of two).  ws_pred / ws_target: [planes, H, W] complex64 each. */
+int ddpmir_freq_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
+                           float* ws_target, double* acc2, ddpmir_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------ */
 /* UNet kernels                                                                                            */
 /* ------------------------------------------------------------------------------------------------------ */

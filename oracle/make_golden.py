@@ -149,10 +149,10 @@ def op_goldens():
     save("ops.npz", **d)
 
 
-def trajectory256():
+def trajectory256(n_images=1):
     fam, q, steps = "webp", 10, 80
     sd = W.make_state_dict(fam, 0)
-    clean = W.synthetic_images(1, 256, 256, seed=1234)
+    clean = W.synthetic_images(n_images, 256, 256, seed=1234)
     y = R.codec_roundtrip(clean, q, "webp")
     t0 = time.time()
     trace = []
@@ -161,8 +161,10 @@ def trajectory256():
         print(f"  step done {time.time() - t0:.0f}s", flush=True)
         return o
     out = R.ddrm_sample(model_fn, y, q, steps, fam, noise_fn=philox_noise, trace=trace)
-    save("traj256_webp.npz", clean_u8=R.quantize_u8(clean), y_u8=R.quantize_u8(y), quality=q, steps=steps,
+    name = "traj256_webp.npz" if n_images == 1 else f"traj256x{n_images}_webp.npz"
+    save(name, clean_u8=R.quantize_u8(clean), y_u8=R.quantize_u8(y), quality=q, steps=steps,
          out=out.half(), psnr_in=R.psnr(y, clean), psnr_out=R.psnr(out, clean),
+         psnr_each=np.array([R.psnr(out[i:i + 1], clean[i:i + 1]) for i in range(n_images)]),
          psnr_trace=np.array([R.psnr(z, clean) for z in trace]), cpu_seconds=time.time() - t0,
          cpu_threads=torch.get_num_threads())
 
@@ -171,11 +173,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--trajectory256", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--images", type=int, default=1)
     args = ap.parse_args()
     if not rl.available():
         sys.exit("reference tree not mounted; goldens can only be minted in the build container")
     if args.trajectory256:
-        trajectory256()
+        trajectory256(args.images)
     else:
         for fn in (op_goldens, unet_goldens, sampler_goldens):
             if not args.only or args.only in fn.__name__:

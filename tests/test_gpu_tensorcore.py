@@ -111,3 +111,29 @@ def test_auto_dispatch_prefers_tensor_core_and_falls_back(ops):
     assert rel(nchw(out), F.conv2d(x, w, padding=1)) < 2e-5
     with pytest.raises(DdpmirError):
         ops.conv3x3(nhwc(x, BF), pack3(w, BF), 64, ops.IMPL_TENSOR)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64, 9), (1, 64, 192, 64, 64, 1), (3, 128, 64, 32, 32, 1), (1, 64, 32, 32, 64, 9),
+                                   (2, 64, 128, 16, 16, 9), (1, 64, 256, 256, 256, 1)])
+def test_streaming_weight_resident_kernel(ops, shape):
+    """The persistent, weight-resident tcgen05 kernel (forced with variant 2) against the tiled one and PyTorch."""
+    from ddpm_image_restoration_b200 import _lib
+    B, Ci, Co, H, W, taps = shape
+    x = bf16_round(torch.randn(B, Ci, H, W, generator=g(1)))
+    ks = 3 if taps == 9 else 1
+    w = bf16_round(torch.randn(Co, Ci, ks, ks, generator=g(2)) / math.sqrt(taps * Ci))
+    b = torch.randn(Co, generator=g(3))
+    res = torch.randn(B, Co, H, W, generator=g(5))
+    ref = F.gelu(F.conv2d(x, w, b, padding=ks // 2)) + res
+    fn = ops.conv3x3 if taps == 9 else ops.gemm
+    pk = pack3(w, BF) if taps == 9 else pack1(w, BF)
+    outs = {}
+    for variant in (1, 2):
+        _lib.lib().ddpmir_igemm_set_variant(variant)
+        try:
+            outs[variant] = fn(nhwc(x, BF), pk, Co, ops.IMPL_TENSOR, out_dtype=torch.float32, bias=b.cuda(), act=ops.ACT_GELU,
+                               res=nhwc(res))
+        finally:
+            _lib.lib().ddpmir_igemm_set_variant(0)
+    assert rel(nchw(outs[2]), ref) < 2e-5
+    assert rel(outs[2], outs[1]) < 1e-6
