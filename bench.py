@@ -289,9 +289,16 @@ def main():
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": f"attn_mma_kernel<hd={64 // heads}> (full-res self-attention, L={H * Wd})",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "peak_source": pk["src"] + " (sustained bf16 GEMM)", "launch_ms": avg_ms,
+                # dram__bytes_read+write of this launch from profiles/r1_ncu_summary.md (ncu --set full, same shape)
+                "traffic": 546.6e6 if (fam == "avif" and bsz == 16 and H * Wd == 65536) else None,
+                "algorithmic_bytes": bsz * H * Wd * 64 * 2 * 4,
+                "peak_source": pk["src"] + " (sustained bf16 GEMM)", "launch_ms": avg_ms,
                 "launches_timed": len(attn), "share_of_step": sum(m for m, _ in attn) / ms,
-                "note": "exp-bound (MUFU/FMA), see DESIGN.md: scores/s = %.3e" % (heads * (H * Wd) ** 2 * bsz / (avg_ms * 1e-3))}
+                "exp_pipe": {"scores_per_s": heads * (H * Wd) ** 2 * bsz / (avg_ms * 1e-3),
+                             "mufu_ceiling_scores_per_s": 16 * 148 * (clk["sm_mhz"] or 1965.0) * 1e6,
+                             "frac": heads * (H * Wd) ** 2 * bsz / (avg_ms * 1e-3) / (16 * 148 * (clk["sm_mhz"] or 1965.0) * 1e6)},
+                "note": "this kernel is bound by the exp (MUFU) + issue pipes, not the tensor pipe: head_dim 8/16 gives 16-32 "
+                        "FLOP per exp; see DESIGN.md section 4 and profiles/r1_ncu_summary.md"}
     unet_tflops = UNET_GF[fam] * B / 1e3 / (ms_per_step / 1e3) if args.res == 256 else None
 
     cpu = None

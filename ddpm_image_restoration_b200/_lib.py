@@ -57,6 +57,26 @@ _SIGNATURES = {
     "ddpmir_avif_combine": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_out_conv_tanh": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
     "ddpmir_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "ddpmir_wgrad": (c_int, [_P, c_int, _P, c_int, _P] + [c_int] * 12 + [_P]),
+    "ddpmir_colsum": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_groupnorm_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
+    "ddpmir_gate_backward": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_lrelu_mask_backward": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_dropout": (c_int, [_P, c_int, _P, c_int, c_int64, c_float, c_uint64, _P]),
+    "ddpmir_maxpool2_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_upsample2_concat_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_attention_train_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_attention_backward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_act_forward": (c_int, [_P, c_int, _P, c_int64, _P]),
+    "ddpmir_act_backward": (c_int, [_P, _P, c_int, _P, c_int64, _P]),
+    "ddpmir_linear_rows_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "ddpmir_conv_input_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ddpmir_out_conv_tanh_backward": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "ddpmir_mse_backward": (c_int, [_P, _P, c_int64, c_float, _P, c_int, _P]),
+    "ddpmir_freq_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
+    "ddpmir_ssim_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
+    "ddpmir_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "ddpmir_adamw_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P, c_float, _P]),
 }
 
 # not part of the public header: tuning hook used by tests/bench

@@ -152,6 +152,63 @@ col_loss_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, in
     }
 }
 
+// backward of the frequency terms: G_k = d/dP_k [ wm (|P|-|T|)^2 + wp (angle P - angle T)^2 ] on the rfft2 half spectrum,
+// then the inverse column transform; the inverse row transform + real part (row_ifft_accum_kernel) finishes
+// d/dp = Re IDFT_unnormalised(G).  Columns > W/2 of wg stay zero (memset by the host wrapper).
+__global__ void __launch_bounds__(FFT_THREADS)
+col_loss_bwd_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, float2* __restrict__ wg, int H, int W,
+                    int cols_per_cta, float w_mag, float w_phase) {
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + FFT_ELEMS;
+    const int p = blockIdx.y;
+    const int half = W / 2 + 1;
+    const int c0 = blockIdx.x * cols_per_cta;
+    const int nb = min(cols_per_cta, half - c0);
+    const float2* pp = wp + (long long)p * H * W;
+    const float2* tp = wt + (long long)p * H * W;
+    for (int i = threadIdx.x; i < nb * H; i += FFT_THREADS) {
+        const int h = i / nb, c = i - h * nb;
+        a[c * H + h] = pp[(long long)h * W + c0 + c];
+        a[(nb + c) * H + h] = tp[(long long)h * W + c0 + c];
+    }
+    __syncthreads();
+    fft_batch(a, b, 2 * nb, H, -1.f);
+    for (int i = threadIdx.x; i < nb * H; i += FFT_THREADS) {
+        const float2 P = a[i], T = a[nb * H + i];
+        const float mp = sqrtf(P.x * P.x + P.y * P.y), mt = sqrtf(T.x * T.x + T.y * T.y);
+        float gx = 0.f, gy = 0.f;
+        if (mp > 0.f) {
+            const float cm = 2.f * w_mag * (mp - mt) / mp;                                  // d|P| = (Re, Im)/|P|
+            const float cp = 2.f * w_phase * (atan2f(P.y, P.x) - atan2f(T.y, T.x)) / (mp * mp);   // d angle = (-Im, Re)/|P|^2
+            gx = cm * P.x - cp * P.y;
+            gy = cm * P.y + cp * P.x;
+        }
+        a[i] = make_float2(gx, gy);
+    }
+    __syncthreads();
+    fft_batch(a, b, nb, H, 1.f);
+    float2* gp = wg + (long long)p * H * W;
+    for (int i = threadIdx.x; i < nb * H; i += FFT_THREADS) {
+        const int h = i / nb, c = i - h * nb;
+        gp[(long long)h * W + c0 + c] = a[c * H + h];
+    }
+}
+
+// out[r, :] += coef * Re(inverse row FFT of ws[r, :])
+__global__ void __launch_bounds__(FFT_THREADS)
+row_ifft_accum_kernel(const float2* __restrict__ ws, float* __restrict__ out, long long rows_total, int W, int rows_per_cta, float coef) {
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + FFT_ELEMS;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const int nb = (int)min((long long)rows_per_cta, rows_total - r0);
+    for (int i = threadIdx.x; i < nb * W; i += FFT_THREADS) a[i] = ws[r0 * W + i];
+    __syncthreads();
+    fft_batch(a, b, nb, W, 1.f);
+    for (int i = threadIdx.x; i < nb * W; i += FFT_THREADS) out[r0 * W + i] += coef * a[i].x;
+}
+
 // forward row FFT of x*0.5+0.5 (the [0,1] images of webp_training.py:111-112)
 __global__ void __launch_bounds__(FFT_THREADS)
 row_fft_affine_kernel(const float* __restrict__ x, float2* __restrict__ ws, long long rows_total, int W, int rows_per_cta) {
@@ -177,6 +234,8 @@ int setup_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(row_ifft_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(col_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(col_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(row_ifft_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(row_fft_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { ddpmir_set_error("fft: shared-memory opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
     done = true;
@@ -249,6 +308,30 @@ extern "C" int ddpmir_freq_loss_terms(const float* pred, const float* target, in
     DDPMIR_LAUNCH_CHECK();
     col_loss_kernel<<<dim3(ceil_div(W / 2 + 1, cpc), planes), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_pred, (const float2*)ws_target,
                                                                                           H, W, cpc, acc2);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+// dpred += d/dpred [ w_mag * sum (|P|-|T|)^2 + w_phase * sum (angle P - angle T)^2 ],  P = rfft2(pred*0.5+0.5)
+extern "C" int ddpmir_freq_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
+                                         float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(pred && target && ws_pred && ws_target && ws_grad && dpred, "freq_loss_backward: null pointer");
+    int rc = check_shape(planes, H, W);
+    if (rc) return rc;
+    if ((rc = setup_smem())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)planes * H;
+    const int rpc = FFT_ELEMS / W;
+    int cpc = FFT_ELEMS / H / 2;
+    if (cpc > 8) cpc = 8;
+    if (cpc < 1) { ddpmir_set_error("freq_loss_backward: H too large"); return DDPMIR_ERR_UNSUPPORTED; }
+    cudaMemsetAsync(ws_grad, 0, sizeof(float2) * rows * W, st);
+    row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(pred, (float2*)ws_pred, rows, W, rpc);
+    row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(target, (float2*)ws_target, rows, W, rpc);
+    col_loss_bwd_kernel<<<dim3(ceil_div(W / 2 + 1, cpc), planes), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_pred, (const float2*)ws_target,
+                                                                                              (float2*)ws_grad, H, W, cpc, w_mag, w_phase);
+    // chain rule of p01 = 0.5 * pred + 0.5
+    row_ifft_accum_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_grad, dpred, rows, W, rpc, 0.5f);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

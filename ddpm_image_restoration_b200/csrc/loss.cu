@@ -91,6 +91,104 @@ ssim_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int
     }
 }
 
+// ---- SSIM backward (d mean-SSIM / dX, Y constant) -----------------------------------------------------------------------
+// pass 1: per output position the partials wrt the three filtered maps that depend on X: mu1, E[X^2], E[XY]
+__global__ void __launch_bounds__(256)
+ssim_bwd_partials_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int W, int clamp01, Gauss g,
+                         float* __restrict__ gmaps /* [planes][3][OH][OW] */) {
+    __shared__ float sx[IN][IN + 1], sy[IN][IN + 1];
+    __shared__ float hf[5][IN][TILE + 1];
+    const int plane = blockIdx.z;
+    const int oh0 = blockIdx.y * TILE, ow0 = blockIdx.x * TILE;
+    const int OH = H - WIN + 1, OW = W - WIN + 1;
+    const float* px = x + (long long)plane * H * W;
+    const float* py = y + (long long)plane * H * W;
+    for (int i = threadIdx.x; i < IN * IN; i += 256) {
+        const int r = i / IN, c = i - r * IN;
+        const int h = oh0 + r, w = ow0 + c;
+        float a = 0.f, b = 0.f;
+        if (h < H && w < W) {
+            a = __fadd_rn(__fmul_rn(px[(long long)h * W + w], 0.5f), 0.5f);
+            b = __fadd_rn(__fmul_rn(py[(long long)h * W + w], 0.5f), 0.5f);
+            if (clamp01) { a = fminf(fmaxf(a, 0.f), 1.f); b = fminf(fmaxf(b, 0.f), 1.f); }
+        }
+        sx[r][c] = a; sy[r][c] = b;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < IN * TILE; i += 256) {
+        const int r = i / TILE, c = i - r * TILE;
+        float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) {
+            const float a = sx[r][c + k], b = sy[r][c + k], wk = g.w[k];
+            m1 = fmaf(wk, a, m1); m2 = fmaf(wk, b, m2);
+            s11 = fmaf(wk, a * a, s11); s22 = fmaf(wk, b * b, s22); s12 = fmaf(wk, a * b, s12);
+        }
+        hf[0][r][c] = m1; hf[1][r][c] = m2; hf[2][r][c] = s11; hf[3][r][c] = s22; hf[4][r][c] = s12;
+    }
+    __syncthreads();
+    const int r = threadIdx.x / TILE, c = threadIdx.x % TILE;
+    if (oh0 + r < OH && ow0 + c < OW) {
+        float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) {
+            const float wk = g.w[k];
+            m1 = fmaf(wk, hf[0][r + k][c], m1); m2 = fmaf(wk, hf[1][r + k][c], m2);
+            e11 = fmaf(wk, hf[2][r + k][c], e11); e22 = fmaf(wk, hf[3][r + k][c], e22); e12 = fmaf(wk, hf[4][r + k][c], e12);
+        }
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const float A1 = 2.f * m1 * m2 + C1, A2 = 2.f * (e12 - m1 * m2) + C2;
+        const float B1 = m1 * m1 + m2 * m2 + C1, B2 = (e11 - m1 * m1) + (e22 - m2 * m2) + C2;
+        const float inv = 1.f / (B1 * B2);
+        const float g_e12 = 2.f * A1 * inv;
+        const float g_e11 = -A1 * A2 * inv / B2;
+        // mu1 enters A1 (2 mu2), A2 (-2 mu2), B1 (2 mu1), B2 (-2 mu1)
+        const float g_mu = (2.f * m2 * A2 - 2.f * m2 * A1) * inv - A1 * A2 * inv * inv * (2.f * m1 * B2 - 2.f * m1 * B1);
+        float* o = gmaps + ((long long)plane * 3) * OH * OW + (long long)(oh0 + r) * OW + (ow0 + c);
+        o[0] = g_mu; o[(long long)OH * OW] = g_e11; o[2LL * OH * OW] = g_e12;
+    }
+}
+
+// pass 2: dX[h,w] += coef * sum_{i,j} g(h-i) g(w-j) [ gmu(i,j) + 2 X gE11(i,j) + Y gE12(i,j) ]  (transpose of the valid filter)
+__global__ void __launch_bounds__(256)
+ssim_bwd_scatter_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gmaps, int planes, int H,
+                        int W, int clamp01, Gauss g, float coef, float* __restrict__ dx) {
+    const int OH = H - WIN + 1, OW = W - WIN + 1;
+    const long long total = (long long)planes * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int plane = (int)(i / ((long long)H * W));
+        const int rem = (int)(i - (long long)plane * H * W);
+        const int h = rem / W, w = rem - h * W;
+        float a = __fadd_rn(__fmul_rn(x[i], 0.5f), 0.5f), b = __fadd_rn(__fmul_rn(y[i], 0.5f), 0.5f);
+        float pass = 1.f;
+        if (clamp01) { if (a <= 0.f || a >= 1.f) pass = 0.f; a = fminf(fmaxf(a, 0.f), 1.f); b = fminf(fmaxf(b, 0.f), 1.f); }
+        const float* gm = gmaps + ((long long)plane * 3) * OH * OW;
+        float s_mu = 0.f, s_11 = 0.f, s_12 = 0.f;
+        for (int u = 0; u < WIN; ++u) {
+            const int oi = h - u;
+            if (oi < 0 || oi >= OH) continue;
+            for (int v = 0; v < WIN; ++v) {
+                const int oj = w - v;
+                if (oj < 0 || oj >= OW) continue;
+                const float wv = g.w[u] * g.w[v];
+                const long long o = (long long)oi * OW + oj;
+                s_mu = fmaf(wv, gm[o], s_mu);
+                s_11 = fmaf(wv, gm[(long long)OH * OW + o], s_11);
+                s_12 = fmaf(wv, gm[2LL * OH * OW + o], s_12);
+            }
+        }
+        dx[i] += coef * pass * (s_mu + 2.f * a * s_11 + b * s_12);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float coef, float* __restrict__ da, long long n, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = coef * (a[i] - b[i]);
+        da[i] = accumulate ? da[i] + v : v;
+    }
+}
+
 __global__ void scale_kernel(const double* __restrict__ acc, double scale, float* __restrict__ out) { out[0] = (float)(acc[0] * scale); }
 
 }  // namespace
@@ -122,6 +220,40 @@ extern "C" int ddpmir_ssim(const float* x, const float* y, int planes, int H, in
     dim3 grid(ceil_div(OW, TILE), ceil_div(OH, TILE), planes);
     ssim_kernel<<<grid, 256, 0, st>>>(x, y, H, W, clamp01, g, ws);
     scale_kernel<<<1, 1, 0, st>>>(ws, 1.0 / ((double)planes * OH * OW), out_scalar);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+// da (+)= weight * d mse(a,b)/da = weight * 2 (a - b) / n
+extern "C" int ddpmir_mse_backward(const float* a, const float* b, int64_t n, float weight, float* da, int accumulate,
+                                   ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(a && b && da && n > 0, "mse_backward: bad arguments");
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    mse_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (float)(2.0 * weight / (double)n), da, n, accumulate);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+// dx += weight * d ssim(x*0.5+0.5, y*0.5+0.5) / dx.   ws: planes * 3 * (H-10) * (W-10) floats.
+extern "C" int ddpmir_ssim_backward(const float* x, const float* y, int planes, int H, int W, int clamp01, float weight, float* dx,
+                                    float* ws, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(x && y && dx && ws && planes > 0 && planes <= 65535, "ssim_backward: bad arguments");
+    DDPMIR_CHECK_ARG(H >= WIN && W >= WIN, "ssim_backward: images must be at least 11x11");
+    Gauss g;
+    double sum = 0;
+    for (int k = 0; k < WIN; ++k) { const double c = k - WIN / 2; g.w[k] = (float)exp(-(c * c) / (2.0 * 1.5 * 1.5)); sum += g.w[k]; }
+    for (int k = 0; k < WIN; ++k) g.w[k] = (float)(g.w[k] / sum);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int OH = H - WIN + 1, OW = W - WIN + 1;
+    dim3 grid(ceil_div(OW, TILE), ceil_div(OH, TILE), planes);
+    ssim_bwd_partials_kernel<<<grid, 256, 0, st>>>(x, y, H, W, clamp01, g, ws);
+    const long long total = (long long)planes * H * W;
+    int g2 = (int)((total + 255) / 256);
+    if (g2 > 148 * 16) g2 = 148 * 16;
+    // mean over planes*OH*OW outputs; chain rule of x01 = 0.5 x + 0.5
+    const float coef = (float)(0.5 * (double)weight / ((double)planes * OH * OW));
+    ssim_bwd_scatter_kernel<<<g2, 256, 0, st>>>(x, y, ws, planes, H, W, clamp01, g, coef, dx);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

@@ -251,6 +251,83 @@ int ddpmir_avif_combine(const void* h, int h_dtype, const void* xt, const float*
 int ddpmir_out_conv_tanh(const void* x, int dtype, int B, int H, int W, int Cin, const float* w, const float* bias,
                          int N, float* out, ddpmir_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------ */
+/* Training step (webp_training.py:476-537): backward kernels.  Gradients are fp32; `dtype` arguments name the   */
+/* dtype of saved activations (operands may be bf16).  Data gradients of conv3x3 / gemm layers reuse the forward */
+/* entry points with transposed, tap-flipped weights.                                                            */
+/* ------------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of conv3x3 (taps = 9) / 1x1 (taps = 1): out += dY^T * im2col(X) for the sub-block
+ * [n_begin, +n_count) x [k_begin, +k_count) of the packed [N, taps*Cin] weight, leading dimension out_ld; oihw = 1
+ * writes the checkpoint's OIHW layout of a 3x3 conv instead.  `out` is accumulated into (zero it for a fresh gradient). */
+int ddpmir_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, float* out, int B, int H, int W, int Cin, int N,
+                 int taps, int n_begin, int n_count, int k_begin, int k_count, int out_ld, int oihw, ddpmir_stream_t stream);
+
+/* Column sums of dY [B*H*W, N] accumulated into out_total[N] and/or out_img[B, N] (bias / time-embedding row-bias
+ * gradients); cls = -1 all pixels, 1 / 0 only low- / high-frequency pixels (the class-dependent second-layer bias of the
+ * stacked gate MLP). */
+int ddpmir_colsum(const void* dy, int dtype, int B, int H, int W, int N, int cls, int bs, int low, float* out_total,
+                  float* out_img, ddpmir_stream_t stream);
+
+/* Backward of y = act(GroupNorm(x)) (act in NONE/GELU/SILU): dx (optionally accumulated), dgamma / dbeta accumulated.
+ * x, dy, dx fp32 NHWC; ws: B*G*2 doubles. */
+int ddpmir_groupnorm_backward(const float* x, const float* dy, int B, int HW, int C, int G, int act, const float* mean_rstd,
+                              const float* gamma, const float* beta, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
+                              double* ws, ddpmir_stream_t stream);
+
+/* Frequency gate e = h3 + g*s*d (g = sigmoid gate, s = 1 | boost[b], webp_inference.py:263-267): dz = de*s*d*g*(1-g),
+ * dd = de*g*s.  g, d in op_dtype. */
+int ddpmir_gate_backward(const float* de, const void* g, const void* d, int op_dtype, const float* boost, float* dz, float* dd,
+                         int B, int H, int W, int C, int bs, int low, ddpmir_stream_t stream);
+
+/* Hidden layer of the stacked gate MLP (freq_mode 1 epilogue): dpre = dg1 * class mask * LeakyReLU'(pre). */
+int ddpmir_lrelu_mask_backward(const float* dg1, const void* g1, int op_dtype, float* dpre, int B, int H, int W, int N, int bs,
+                               int low, ddpmir_stream_t stream);
+
+/* nn.Dropout(p) in train mode (webp_inference.py:291,313): out = keep ? in/(1-p) : 0 with a counter-hash mask keyed by
+ * (seed, element); applying it to the incoming gradient with the same seed is its backward. */
+int ddpmir_dropout(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, float p, uint64_t seed,
+                   ddpmir_stream_t stream);
+
+int ddpmir_maxpool2_backward(const float* x, const float* dy, float* dx, int B, int H, int W, int C, ddpmir_stream_t stream);
+int ddpmir_upsample2_concat_backward(const float* dy, float* dlo, float* dskip, int B, int H, int W, int C1, int C2,
+                                     ddpmir_stream_t stream);
+
+/* Attention for training: forward that also returns the row log-sum-exp lse [B, heads, L], and the backward
+ * dqkv [B, L, 3C] fp32 from (qkv, o, dout, lse); delta is a [B, heads, L] fp32 workspace. */
+int ddpmir_attention_train_forward(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float* lse,
+                                   ddpmir_stream_t stream);
+int ddpmir_attention_backward(const void* qkv, const void* o, int dtype, const float* dout, const float* lse, float* delta,
+                              float* dqkv, int B, int L, int C, int heads, ddpmir_stream_t stream);
+
+/* Small fp32 layers: element-wise activation forward / backward (u = pre-activation), row-wise linear backward
+ * (dx may be NULL; dw, db accumulated), the 3-channel input convolution (weight gradient in OIHW + the gradients of the
+ * folded GroupNorm affine; bias via ddpmir_colsum) and the out_conv + tanh tail. */
+int ddpmir_act_forward(const float* x, int act, float* out, int64_t n, ddpmir_stream_t stream);
+int ddpmir_act_backward(const float* dy, const float* u, int act, float* dx, int64_t n, ddpmir_stream_t stream);
+int ddpmir_linear_rows_backward(const float* dy, const float* x, const float* w, int rows, int K, int N, float* dx, float* dw,
+                                float* db, ddpmir_stream_t stream);
+int ddpmir_conv_input_backward(const float* x, const float* dh, int B, int Cin, int H, int W, int N, int ksize, const float* w,
+                               const float* mean_rstd, const float* gamma, const float* beta, float* dw, float* dgamma,
+                               float* dbeta, ddpmir_stream_t stream);
+int ddpmir_out_conv_tanh_backward(const void* a, int dtype, const float* y, const float* dy, int B, int H, int W, int Cin, int N,
+                                  const float* w, float* da, float* dw, float* dbias, ddpmir_stream_t stream);
+
+/* Loss backward pieces of frequency_aware_loss (webp_training.py:105-132): da (+)= weight * d mse / da;
+ * dpred += d/dpred [w_mag * sum (|P|-|T|)^2 + w_phase * sum (angle P - angle T)^2] (ws_*: [planes,H,W] complex64);
+ * dx += weight * d ssim / dx (ws: planes*3*(H-10)*(W-10) floats). */
+int ddpmir_mse_backward(const float* a, const float* b, int64_t n, float weight, float* da, int accumulate, ddpmir_stream_t stream);
+int ddpmir_freq_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
+                              float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream);
+int ddpmir_ssim_backward(const float* x, const float* y, int planes, int H, int W, int clamp01, float weight, float* dx, float* ws,
+                         ddpmir_stream_t stream);
+
+/* Optimiser (webp_training.py:521-524, 775): acc += sum x^2 (global gradient norm), and the fused
+ * clip_grad_norm_(max_norm) + AdamW update of one tensor (grad_sumsq NULL = no clipping; step >= 1). */
+int ddpmir_sumsq(const float* x, int64_t n, double* acc, ddpmir_stream_t stream);
+int ddpmir_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, const double* grad_sumsq, float max_norm, ddpmir_stream_t stream);
+
 /* dtype conversion helper for weight pre-packing (fp32 -> bf16, round-to-nearest-even). */
 int ddpmir_cast_f32_to_bf16(const float* in, void* out, int64_t n, ddpmir_stream_t stream);
 

@@ -1,0 +1,223 @@
+"""Backward kernels of the training step against torch.autograd on the CPU (fp32), one test per kernel."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restated as R
+from util import bf16_round, nchw, nhwc, pack1, pack3, rel
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ddpm_image_restoration_b200 import ops as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def T():
+    from ddpm_image_restoration_b200 import ops_train as t
+    return t
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=g(seed)) * scale
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128, 8, 8, 9), (1, 128, 64, 4, 6, 9), (2, 64, 192, 16, 16, 1), (3, 32, 48, 5, 5, 9)])
+def test_wgrad_colsum_and_dgrad(ops, T, shape):
+    B, Ci, Co, H, W, taps = shape
+    ks = 3 if taps == 9 else 1
+    x = rnd(B, Ci, H, W, seed=1).requires_grad_()
+    w = (rnd(Co, Ci, ks, ks, seed=2) / math.sqrt(taps * Ci)).requires_grad_()
+    b = rnd(Co, seed=3).requires_grad_()
+    dy = rnd(B, Co, H, W, seed=4)
+    F.conv2d(x, w, b, padding=ks // 2).backward(dy)
+    dw = torch.zeros(Co, Ci, ks, ks).cuda()
+    T.wgrad(nhwc(dy), nhwc(x.detach()), dw, taps, oihw=(taps == 9))
+    assert rel(dw.cpu(), w.grad) < 1e-5
+    # sub-block into a packed buffer (rows 16.., second half of K)
+    K = taps * Ci
+    sub = torch.zeros(Co - 16, K // 2).cuda()
+    T.wgrad(nhwc(dy), nhwc(x.detach()), sub, taps, n_begin=16, n_count=Co - 16, k_begin=K // 2, k_count=K // 2)
+    packed = w.grad.permute(0, 2, 3, 1).reshape(Co, K)
+    assert rel(sub.cpu(), packed[16:, K // 2:]) < 1e-5
+    db = torch.zeros(Co).cuda(); dimg = torch.zeros(B, Co).cuda()
+    T.colsum(nhwc(dy), db, dimg)
+    assert rel(db.cpu(), b.grad) < 1e-5 and rel(dimg.cpu(), dy.sum((2, 3))) < 1e-5
+    # data gradient = the forward kernel on flipped / transposed weights
+    wt = w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, taps * Co).contiguous().cuda()
+    fn = ops.conv3x3 if taps == 9 else ops.gemm
+    if Co % 16 == 0:
+        dx = fn(nhwc(dy), wt, Ci, ops.IMPL_SIMT)
+        assert rel(nchw(dx), x.grad) < 1e-5
+
+
+def test_colsum_class_split(T):
+    B, N, H, W = 2, 32, 8, 12
+    dy = rnd(B, N, H, W, seed=1)
+    m = R.low_mask(H, W, 4, 3).float()
+    lo = torch.zeros(N).cuda(); hi = torch.zeros(N).cuda()
+    T.colsum(nhwc(dy), lo, None, cls=1, bs=4, low=3)
+    T.colsum(nhwc(dy), hi, None, cls=0, bs=4, low=3)
+    assert rel(lo.cpu(), (dy * m).sum((0, 2, 3))) < 1e-5 and rel(hi.cpu(), (dy * (1 - m)).sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("act,fn", [(0, lambda v: v), (5, F.gelu), (4, F.silu)])
+def test_groupnorm_backward(ops, T, act, fn):
+    B, C, H, W = 2, 64, 6, 10
+    x = (rnd(B, C, H, W, seed=1) * 2 + 0.5).requires_grad_()
+    gamma, beta = rnd(C, seed=2).requires_grad_(), rnd(C, seed=3).requires_grad_()
+    dy = rnd(B, C, H, W, seed=4)
+    fn(F.group_norm(x, 8, gamma, beta, 1e-5)).backward(dy)
+    st = ops.groupnorm_stats(nhwc(x.detach()), 8)
+    dgamma, dbeta = torch.zeros(C).cuda(), torch.zeros(C).cuda()
+    dx = T.groupnorm_backward(nhwc(x.detach()), nhwc(dy), st, gamma.detach().cuda(), beta.detach().cuda(), act, dgamma, dbeta)
+    assert rel(nchw(dx), x.grad) < 2e-5
+    assert rel(dgamma.cpu(), gamma.grad) < 2e-5 and rel(dbeta.cpu(), beta.grad) < 2e-5
+
+
+def test_gate_and_lrelu_mask_backward(T):
+    B, C, H, W, bs, low = 2, 64, 8, 8, 4, 3
+    m = R.low_mask(H, W, bs, low).float()
+    h3 = rnd(B, C, H, W, seed=1)
+    d = rnd(B, C, H, W, seed=2).requires_grad_()
+    z = rnd(B, C, H, W, seed=3).requires_grad_()
+    boost = torch.tensor([0.7, 0.2])
+    s = torch.where(m.bool(), torch.ones(1), boost.view(B, 1, 1, 1))
+    e = h3 + torch.sigmoid(z) * s * d
+    de = rnd(B, C, H, W, seed=4)
+    e.backward(de)
+    dz, dd = T.gate_backward(nhwc(de), nhwc(torch.sigmoid(z.detach())), nhwc(d.detach()), boost.cuda(), bs, low)
+    assert rel(nchw(dz), z.grad) < 1e-5 and rel(nchw(dd), d.grad) < 1e-5
+    pre = rnd(B, C, H, W, seed=5).requires_grad_()
+    hid = F.leaky_relu(pre, 0.2)
+    g1 = torch.cat([hid[:, :C // 2] * m, hid[:, C // 2:] * (1 - m)], 1)
+    dg1 = rnd(B, C, H, W, seed=6)
+    g1.backward(dg1)
+    dpre = T.lrelu_mask_backward(nhwc(dg1), nhwc(g1.detach()), bs, low)
+    assert rel(nchw(dpre), pre.grad) < 1e-6
+
+
+def test_dropout_is_its_own_backward(T):
+    x = rnd(4, 8, 8, 64, seed=1).cuda()
+    y = T.dropout(x, 0.1, seed=5)
+    keep = (y != 0)
+    assert abs(float(keep.float().mean()) - 0.9) < 0.02
+    assert torch.allclose(y[keep], x[keep] / 0.9)
+    assert torch.equal(T.dropout(x, 0.1, seed=5), y) and not torch.equal(T.dropout(x, 0.1, seed=6), y)
+    assert torch.equal(T.dropout(x, 0.0, seed=5), x)
+
+
+def test_pool_and_upsample_backward(T):
+    x = rnd(2, 16, 8, 12, seed=1).requires_grad_()
+    dy = rnd(2, 16, 4, 6, seed=2)
+    F.max_pool2d(x, 2).backward(dy)
+    assert torch.equal(nchw(T.maxpool2_backward(nhwc(x.detach()), nhwc(dy))), x.grad)
+    for hw in ((4, 6), (1, 1), (2, 1)):
+        lo = rnd(2, 16, *hw, seed=3).requires_grad_()
+        skip = rnd(2, 8, 2 * hw[0], 2 * hw[1], seed=4).requires_grad_()
+        out = torch.cat([F.interpolate(lo, scale_factor=2, mode="bilinear", align_corners=False), skip], 1)
+        dy = rnd(*out.shape, seed=5)
+        out.backward(dy)
+        dlo, dskip = T.upsample2_concat_backward(nhwc(dy), 16)
+        assert rel(nchw(dlo), lo.grad) < 1e-6 and torch.equal(nchw(dskip), skip.grad)
+
+
+@pytest.mark.parametrize("hd,heads,L", [(16, 4, 64), (8, 8, 100), (32, 4, 33), (64, 2, 16), (128, 2, 8), (256, 2, 4)])
+def test_attention_backward(T, hd, heads, L):
+    C = hd * heads
+    qkv = rnd(2, L, 3 * C, seed=hd + L).requires_grad_()
+    q, k, v = qkv.view(2, L, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(2, L, C)
+    do = rnd(2, L, C, seed=7)
+    o.backward(do)
+    out, lse = T.attention_train_forward(qkv.detach().cuda(), heads)
+    assert rel(out.cpu(), o.detach()) < 1e-5
+    dqkv = T.attention_backward(qkv.detach().cuda(), out, do.cuda(), lse, heads)
+    assert rel(dqkv.cpu(), qkv.grad) < 2e-5
+
+
+def test_small_layers_backward(ops, T):
+    # row-wise linear + SiLU (time embedding MLP)
+    x = rnd(4, 256, seed=1).requires_grad_()
+    w = (rnd(1024, 256, seed=2) / 16).requires_grad_(); b = rnd(1024, seed=3).requires_grad_()
+    u = F.linear(x, w, b)
+    y = F.silu(u)
+    dy = rnd(4, 1024, seed=4)
+    y.backward(dy)
+    du = T.act_backward(dy.cuda(), u.detach().cuda(), ops.ACT_SILU)
+    dw, db = torch.zeros(1024, 256).cuda(), torch.zeros(1024).cuda()
+    dx = T.linear_rows_backward(du, x.detach().cuda(), w.detach().cuda(), dw, db)
+    assert rel(dx.cpu(), x.grad) < 1e-5 and rel(dw.cpu(), w.grad) < 1e-5 and rel(db.cpu(), b.grad) < 1e-5
+    assert rel(T.act_forward(u.detach().cuda(), ops.ACT_SILU).cpu(), y.detach()) < 1e-6
+    # input conv with folded GroupNorm
+    img = (rnd(2, 3, 16, 16, seed=5) * 0.6).requires_grad_(False)
+    gamma, beta = rnd(3, seed=6).requires_grad_(), rnd(3, seed=7).requires_grad_()
+    wc = (rnd(64, 3, 3, 3, seed=8) / 5).requires_grad_()
+    h = F.conv2d(F.group_norm(img, 3, gamma, beta, 1e-5), wc, None, padding=1)
+    dh = rnd(2, 64, 16, 16, seed=9)
+    h.backward(dh)
+    st = ops.groupnorm_stats(img.cuda(), 3, nchw=True)
+    dwc, dga, dbe = torch.zeros(64, 3, 3, 3).cuda(), torch.zeros(3).cuda(), torch.zeros(3).cuda()
+    T.conv_input_backward(img.cuda(), nhwc(dh), wc.detach().cuda(), dwc, st, gamma.detach().cuda(), beta.detach().cuda(), dga, dbe)
+    assert rel(dwc.cpu(), wc.grad) < 1e-5 and rel(dga.cpu(), gamma.grad) < 1e-5 and rel(dbe.cpu(), beta.grad) < 1e-5
+    w1 = rnd(64, 3, 1, 1, seed=10).requires_grad_()
+    F.conv2d(img, w1).backward(dh)
+    dw1 = torch.zeros(64, 3, 1, 1).cuda()
+    T.conv_input_backward(img.cuda(), nhwc(dh), w1.detach().cuda(), dw1)
+    assert rel(dw1.cpu(), w1.grad) < 1e-5
+    # out_conv + tanh
+    a = rnd(2, 64, 12, 12, seed=11).requires_grad_()
+    wo = (rnd(3, 64, 3, 3, seed=12) / 24).requires_grad_(); bo = rnd(3, seed=13).requires_grad_()
+    yv = torch.tanh(F.conv2d(a, wo, bo, padding=1))
+    dyo = rnd(2, 3, 12, 12, seed=14)
+    yv.backward(dyo)
+    dwo, dbo = torch.zeros(3, 64, 3, 3).cuda(), torch.zeros(3).cuda()
+    da = T.out_conv_tanh_backward(nhwc(a.detach()), yv.detach().cuda(), dyo.cuda(), wo.detach().cuda(), dwo, dbo)
+    assert rel(nchw(da), a.grad) < 1e-5 and rel(dwo.cpu(), wo.grad) < 1e-5 and rel(dbo.cpu(), bo.grad) < 1e-5
+
+
+def test_frequency_aware_loss_backward(T):
+    gen = g(3)
+    target = torch.rand(2, 3, 32, 32, generator=gen) * 2 - 1
+    pred = (target + 0.2 * torch.randn(2, 3, 32, 32, generator=gen)).requires_grad_()
+    p01, t01 = pred * 0.5 + 0.5, target * 0.5 + 0.5
+    freq = 0
+    for c in range(3):
+        fp, ft = torch.fft.rfft2(p01[:, c]), torch.fft.rfft2(t01[:, c])
+        freq = freq + F.mse_loss(fp.abs(), ft.abs()) + 0.5 * F.mse_loss(torch.angle(fp), torch.angle(ft))
+    loss = F.mse_loss(pred, target) + 0.5 * freq + 0.3 * (1 - R.ssim(p01, t01, 1.0))
+    loss.backward()
+    got = T.frequency_aware_loss_backward(pred.detach().cuda(), target.cuda()).cpu()
+    assert rel(got, pred.grad) < 2e-3      # the phase term's gradient ~ 1/|P| is ill-conditioned at small coefficients
+
+
+def test_adamw_and_clip(T):
+    torch.manual_seed(0)
+    ps = [torch.randn(1000), torch.randn(37, 5)]
+    gs = [torch.randn(1000) * 3, torch.randn(37, 5)]
+    ref = [p.clone().requires_grad_() for p in ps]
+    opt = torch.optim.AdamW(ref, lr=2e-4, weight_decay=1e-5, betas=(0.9, 0.99))
+    dev = [p.clone().cuda() for p in ps]
+    ms = [torch.zeros_like(p) for p in dev]; vs = [torch.zeros_like(p) for p in dev]
+    for step in (1, 2, 3):
+        for r, gr in zip(ref, gs):
+            r.grad = gr.clone() * step
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        opt.step()
+        acc = torch.zeros(1, dtype=torch.float64).cuda()
+        gd = [(gr * step).cuda() for gr in gs]
+        for gg in gd:
+            T.sumsq(gg, acc)
+        for p, gg, m, v in zip(dev, gd, ms, vs):
+            T.adamw_step(p, gg, m, v, 2e-4, 0.9, 0.99, 1e-8, 1e-5, step, acc, 1.0)
+    for p, r in zip(dev, ref):
+        assert rel(p.cpu(), r.detach()) < 1e-6
