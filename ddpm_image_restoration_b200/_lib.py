@@ -58,7 +58,8 @@ _SIGNATURES = {
     "ddpmir_out_conv_tanh": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
     "ddpmir_cast_f32_to_bf16": (c_int, [_P, _P, c_int64, _P]),
     "ddpmir_wgrad": (c_int, [_P, c_int, _P, c_int, _P] + [c_int] * 12 + [_P]),
-    "ddpmir_colsum": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_colsum": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_time_features": (c_int, [_P, c_int, c_int, _P, _P]),
     "ddpmir_groupnorm_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
     "ddpmir_gate_backward": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_lrelu_mask_backward": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -69,7 +70,7 @@ _SIGNATURES = {
     "ddpmir_attention_backward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_act_forward": (c_int, [_P, c_int, _P, c_int64, _P]),
     "ddpmir_act_backward": (c_int, [_P, _P, c_int, _P, c_int64, _P]),
-    "ddpmir_linear_rows_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "ddpmir_linear_rows_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),
     "ddpmir_conv_input_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ddpmir_out_conv_tanh_backward": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "ddpmir_mse_backward": (c_int, [_P, _P, c_int64, c_float, _P, c_int, _P]),

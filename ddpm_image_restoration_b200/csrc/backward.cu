@@ -85,11 +85,14 @@ wgrad_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__
 // out_total[n] += sum_m sel(m) dY[m,n];  out_img[b,n] += the same per image.  cls: -1 all rows, 0 high-frequency rows
 // only, 1 low-frequency rows only (is_low_freq of the pixel).
 __global__ void __launch_bounds__(256)
-colsum_kernel(const void* __restrict__ dy, int dtype, long long M, int N, int H, int W, int cls, int bs, int low,
-              float* __restrict__ out_total, float* __restrict__ out_img, int rows_per_cta) {
+colsum_kernel(const void* __restrict__ dy, int dtype, long long M, int N, int H, int W, int cls, int bs, int low, int n_begin,
+              int n_count, float* __restrict__ out_total, float* __restrict__ out_img, int rows_per_cta) {
     const int hw = H * W;
     const long long m0 = (long long)blockIdx.x * rows_per_cta;
     const long long m1 = min(M, m0 + rows_per_cta);
+    dy = dtype == DDPMIR_F32 ? (const void*)((const float*)dy + n_begin) : (const void*)((const bf16*)dy + n_begin);
+    const int ldn = N;
+    N = n_count;
     for (int n = threadIdx.x; n < N; n += 256) {
         float s = 0.f;
         int cur_b = (int)(m0 / hw);
@@ -105,7 +108,7 @@ colsum_kernel(const void* __restrict__ dy, int dtype, long long M, int N, int H,
                 const int h = rem / W, w = rem - h * W;
                 if ((int)is_low_freq(h, w, H, W, bs, low) != cls) continue;
             }
-            s += ld_any(dy, dtype, m * N + n);
+            s += ld_any(dy, dtype, m * ldn + n);
         }
         if (out_img) atomicAdd(&out_img[(long long)cur_b * N + n], s);
         if (out_total) atomicAdd(&out_total[n], s);
@@ -327,14 +330,16 @@ extern "C" int ddpmir_wgrad(const void* dy, int dy_dtype, const void* x, int x_d
     return DDPMIR_OK;
 }
 
-extern "C" int ddpmir_colsum(const void* dy, int dtype, int B, int H, int W, int N, int cls, int bs, int low, float* out_total,
-                             float* out_img, ddpmir_stream_t stream) {
+extern "C" int ddpmir_colsum(const void* dy, int dtype, int B, int H, int W, int N, int cls, int bs, int low, int n_begin,
+                             int n_count, float* out_total, float* out_img, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(dy && (out_total || out_img), "colsum: null pointer");
+    DDPMIR_CHECK_ARG(n_begin >= 0 && n_count > 0 && n_begin + n_count <= N, "colsum: bad column range");
     DDPMIR_CHECK_ARG(cls < 0 || (bs > 0 && low > 0), "colsum: class split needs bs/low");
     const long long M = (long long)B * H * W;
     int rows = (int)((M + 148 * 4 - 1) / (148 * 4));
     if (rows < 8) rows = 8;
-    colsum_kernel<<<ceil_div(M, rows), 256, 0, (cudaStream_t)stream>>>(dy, dtype, M, N, H, W, cls, bs, low, out_total, out_img, rows);
+    colsum_kernel<<<ceil_div(M, rows), 256, 0, (cudaStream_t)stream>>>(dy, dtype, M, N, H, W, cls, bs, low, n_begin, n_count, out_total,
+                                                                     out_img, rows);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

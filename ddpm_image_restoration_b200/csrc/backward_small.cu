@@ -29,10 +29,11 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 }
 
 // dx[r,k] = sum_n dy[r,n] W[n,k]
-__global__ void linear_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int R, int K, int N) {
+__global__ void linear_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int R, int K, int N,
+                                 int accumulate) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (k >= K) return;
-    float s = 0.f;
+    float s = accumulate ? dx[(long long)r * K + k] : 0.f;
     for (int n = 0; n < N; ++n) s = fmaf(dy[(long long)r * N + n], w[(long long)n * K + k], s);
     dx[(long long)r * K + k] = s;
 }
@@ -229,10 +230,10 @@ extern "C" int ddpmir_act_backward(const float* dy, const float* u, int act, flo
 }
 
 extern "C" int ddpmir_linear_rows_backward(const float* dy, const float* x, const float* w, int rows, int K, int N, float* dx,
-                                           float* dw, float* db, ddpmir_stream_t stream) {
+                                           int accumulate_dx, float* dw, float* db, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(dy && x && w && rows > 0 && K > 0 && N > 0 && rows <= 65535 && N <= 65535, "linear_rows_backward: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dx) linear_dx_kernel<<<dim3(ceil_div(K, 128), rows), 128, 0, st>>>(dy, w, dx, rows, K, N);
+    if (dx) linear_dx_kernel<<<dim3(ceil_div(K, 128), rows), 128, 0, st>>>(dy, w, dx, rows, K, N, accumulate_dx);
     if (dw) linear_dw_kernel<<<dim3(ceil_div(K, 128), N), 128, 0, st>>>(dy, x, dw, db, rows, K, N);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;

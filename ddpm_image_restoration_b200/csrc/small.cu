@@ -44,6 +44,13 @@ extern "C" int ddpmir_linear_rows(const float* in, int rows, int K, const float*
     return DDPMIR_OK;
 }
 
+extern "C" int ddpmir_time_features(const float* t, int B, int dim, float* out, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(t && out && B > 0 && dim >= 4 && dim % 2 == 0, "time_features: bad arguments");
+    time_features_kernel<<<ceil_div((long long)B * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, B, dim, out);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
 extern "C" int ddpmir_time_embed(const float* t, int B, int dim, const float* w0, const float* b0, const float* w1,
                                  const float* b1, float* ws, float* out, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(t && w0 && b0 && w1 && b1 && ws && out && B > 0 && dim >= 4 && dim % 2 == 0, "time_embed: bad arguments");

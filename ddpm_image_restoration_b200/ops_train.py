@@ -21,10 +21,11 @@ def wgrad(dy, x, out, taps, n_begin=0, n_count=None, k_begin=0, k_count=None, ou
     LAUNCHES[0] += 1
 
 
-def colsum(dy, out_total=None, out_img=None, cls=-1, bs=0, low=0):
+def colsum(dy, out_total=None, out_img=None, cls=-1, bs=0, low=0, n_begin=0, n_count=None):
     B, H, W, N = dy.shape
-    _lib.check(_lib.lib().ddpmir_colsum(_p(dy), _code(dy.dtype), B, H, W, N, cls, bs, low, _p(out_total), _p(out_img), _stream()),
-               "colsum")
+    n_count = N - n_begin if n_count is None else n_count
+    _lib.check(_lib.lib().ddpmir_colsum(_p(dy), _code(dy.dtype), B, H, W, N, cls, bs, low, n_begin, n_count, _p(out_total),
+                                        _p(out_img), _stream()), "colsum")
     LAUNCHES[0] += 1
 
 
@@ -110,6 +111,13 @@ def attention_backward(qkv, o, dout, lse, heads):
     return dqkv
 
 
+def time_features(t, dim=256):
+    out = torch.empty((t.shape[0], dim), dtype=F32, device=t.device)
+    _lib.check(_lib.lib().ddpmir_time_features(_p(_f32(t, "t")), t.shape[0], dim, _p(out), _stream()), "time_features")
+    LAUNCHES[0] += 1
+    return out
+
+
 def act_forward(x, act):
     out = torch.empty_like(x)
     _lib.check(_lib.lib().ddpmir_act_forward(_p(_f32(x, "x")), act, _p(out), x.numel(), _stream()), "act_forward")
@@ -124,12 +132,13 @@ def act_backward(dy, u, act):
     return dx
 
 
-def linear_rows_backward(dy, x, w, dw=None, db=None, need_dx=True):
+def linear_rows_backward(dy, x, w, dw=None, db=None, need_dx=True, dx_accum=None):
+    """dx = dy W (or dx_accum += dy W), dw += dy^T x, db += colsum(dy)."""
     rows, N = dy.shape
     K = x.shape[1]
-    dx = torch.empty((rows, K), dtype=F32, device=dy.device) if need_dx else None
-    _lib.check(_lib.lib().ddpmir_linear_rows_backward(_p(_f32(dy, "dy")), _p(_f32(x, "x")), _p(_f32(w, "w")), rows, K, N, _p(dx), _p(dw),
-                                                      _p(db), _stream()), "linear_rows_backward")
+    dx = dx_accum if dx_accum is not None else (torch.empty((rows, K), dtype=F32, device=dy.device) if need_dx else None)
+    _lib.check(_lib.lib().ddpmir_linear_rows_backward(_p(_f32(dy, "dy")), _p(_f32(x, "x")), _p(_f32(w, "w")), rows, K, N, _p(dx),
+                                                      int(dx_accum is not None), _p(dw), _p(db), _stream()), "linear_rows_backward")
     LAUNCHES[0] += 2
     return dx
 

@@ -40,3 +40,14 @@ def sum_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def allreduce_mean_(flat):
+    """In-place mean over ranks of one flat tensor (the training step's single gradient collective; NCCL over
+    NVLink on the GPUs, gloo in the CPU tests).  Identity when torch.distributed is not initialised."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.mul_(1.0 / dist.get_world_size())
+    return flat

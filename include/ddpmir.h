@@ -146,6 +146,9 @@ int ddpmir_freq_loss_terms(const float* pred, const float* target, int planes, i
 int ddpmir_time_embed(const float* t, int B, int dim, const float* w0, const float* b0, const float* w1,
                       const float* b1, float* ws, float* out, ddpmir_stream_t stream);
 
+/* Only the sinusoidal features [B, dim] of TimeEmbedding (the training step keeps the MLP's pre-activations). */
+int ddpmir_time_features(const float* t, int B, int dim, float* out, ddpmir_stream_t stream);
+
 /* out[r, n] = act(bias[n] + sum_k in[r,k] * w[n,k]) for a few rows (time_proj webp_inference.py:308; the pooled
  * multi-scale gates avif_inference.py:193-201).  All fp32. */
 int ddpmir_linear_rows(const float* in, int rows, int K, const float* w, const float* bias, int N, int act,
@@ -265,9 +268,9 @@ int ddpmir_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, float
 
 /* Column sums of dY [B*H*W, N] accumulated into out_total[N] and/or out_img[B, N] (bias / time-embedding row-bias
  * gradients); cls = -1 all pixels, 1 / 0 only low- / high-frequency pixels (the class-dependent second-layer bias of the
- * stacked gate MLP). */
-int ddpmir_colsum(const void* dy, int dtype, int B, int H, int W, int N, int cls, int bs, int low, float* out_total,
-                  float* out_img, ddpmir_stream_t stream);
+ * stacked gate MLP).  Only columns [n_begin, n_begin + n_count) are summed; outputs are indexed from 0. */
+int ddpmir_colsum(const void* dy, int dtype, int B, int H, int W, int N, int cls, int bs, int low, int n_begin, int n_count,
+                  float* out_total, float* out_img, ddpmir_stream_t stream);
 
 /* Backward of y = act(GroupNorm(x)) (act in NONE/GELU/SILU): dx (optionally accumulated), dgamma / dbeta accumulated.
  * x, dy, dx fp32 NHWC; ws: B*G*2 doubles. */
@@ -305,8 +308,8 @@ int ddpmir_attention_backward(const void* qkv, const void* o, int dtype, const f
  * folded GroupNorm affine; bias via ddpmir_colsum) and the out_conv + tanh tail. */
 int ddpmir_act_forward(const float* x, int act, float* out, int64_t n, ddpmir_stream_t stream);
 int ddpmir_act_backward(const float* dy, const float* u, int act, float* dx, int64_t n, ddpmir_stream_t stream);
-int ddpmir_linear_rows_backward(const float* dy, const float* x, const float* w, int rows, int K, int N, float* dx, float* dw,
-                                float* db, ddpmir_stream_t stream);
+int ddpmir_linear_rows_backward(const float* dy, const float* x, const float* w, int rows, int K, int N, float* dx,
+                                int accumulate_dx, float* dw, float* db, ddpmir_stream_t stream);
 int ddpmir_conv_input_backward(const float* x, const float* dh, int B, int Cin, int H, int W, int N, int ksize, const float* w,
                                const float* mean_rstd, const float* gamma, const float* beta, float* dw, float* dgamma,
                                float* dbeta, ddpmir_stream_t stream);

@@ -205,13 +205,13 @@ def _up_cat(a: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
 
 
 def unet_forward(sd: SD, x: torch.Tensor, t: torch.Tensor, level: Optional[torch.Tensor] = None,
-                 family: str = "webp", taps: Optional[dict] = None) -> torch.Tensor:
+                 family: str = "webp", taps: Optional[dict] = None, enable_grad: bool = False) -> torch.Tensor:
     """{WebP,JPEG,AVIF}DiffusionModel.forward webp_inference.py:369-399 / avif_inference.py:355-385.
 
     `taps` (optional dict) receives the output of every block, for per-layer parity checks.
     """
     fam = FAMILY[family]
-    with torch.no_grad():
+    with (torch.enable_grad() if enable_grad else torch.no_grad()):
         t_emb = time_embedding(sd, t)
         if level is None:
             level = t.clone()
@@ -406,6 +406,26 @@ def ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0) -> torch.Ten
     cs = (2 * s12 + C2) / (s11 + s22 + C2)
     sm = ((2 * mu1 * mu2 + C1) / (mu1 * mu1 + mu2 * mu2 + C1)) * cs
     return sm.flatten(2).mean(-1).mean()
+
+
+def frequency_aware_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """webp_training.py:105-132 (SSIM restated, see `ssim`)."""
+    spatial = F.mse_loss(pred, target)
+    p01, t01 = pred * 0.5 + 0.5, target * 0.5 + 0.5
+    freq = 0
+    for c in range(3):
+        fp, ft = torch.fft.rfft2(p01[:, c]), torch.fft.rfft2(t01[:, c])
+        freq = freq + F.mse_loss(torch.abs(fp), torch.abs(ft)) + 0.5 * F.mse_loss(torch.angle(fp), torch.angle(ft))
+    return spatial + 0.5 * freq + 0.3 * (1.0 - ssim(p01, t01, 1.0))
+
+
+def training_step_reference(sd: SD, xt, t, x0, family: str = "webp"):
+    """Loss and gradients of one training step (webp_training.py:511-521, dropout disabled) by torch.autograd."""
+    params = {k: (v.clone().requires_grad_() if v.dtype.is_floating_point and not k.endswith("dct_matrix") else v) for k, v in sd.items()}
+    pred = unet_forward(params, xt, t, t.clone(), family, enable_grad=True)
+    loss = frequency_aware_loss(xt + pred, x0)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
 
 
 def color_l1(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -67,8 +67,11 @@ def test_shard_range():
 def _rank_main(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
-    from ddpm_image_restoration_b200.parallel import max_over_ranks, shard_range, sum_over_ranks
+    from ddpm_image_restoration_b200.parallel import allreduce_mean_, max_over_ranks, shard_range, sum_over_ranks
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.full((1000,), float(rank + 1))      # the training step's flat gradient buffer
+    allreduce_mean_(flat)
+    assert torch.allclose(flat, torch.full((1000,), 1.5))
     lo, hi = shard_range(10, rank, world)
     dist.barrier()
     t = max_over_ranks(1.0 + rank)            # the slowest rank defines the step time
