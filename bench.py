@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample = the headline DDRM restoration loop (BASELINE configs[1]); train = BASELINE configs[3], "
+                         "one webp_training.py optimizer step per step (WebP UNet 64x64, batch 32/GPU, NCCL gradient all-reduce)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
     return ap.parse_args()
 
@@ -166,10 +169,78 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args):
+    """BASELINE configs[3]: webp_training.py training step, bf16 operands, batch 256 sharded over 8 GPUs (32 per GPU,
+    weak scaling), one NCCL all-reduce of the flat fp32 gradient per step.  Secondary line (not the headline metric)."""
+    import torch
+    import torch.distributed as dist
+    import ddpm_image_restoration_b200 as P
+    from ddpm_image_restoration_b200 import codec, ops
+    from ddpm_image_restoration_b200.training import Trainer
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Bn, res = (args.batch if args.batch != 64 else 32), (args.res if args.res != 256 else 64)
+    torch.manual_seed(0)
+    model = P.WebPDiffusionModel().to(dev).set_precision("bf16")
+    tr = Trainer(model, seed=rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    x0 = (torch.rand(Bn, 3, res, res, generator=g) * 2 - 1)
+    xt = codec.webp_compress(x0, 30).contiguous().pin_memory()
+    x0 = x0.pin_memory()
+    t = (torch.randint(1, 100, (Bn,), generator=g).float() / 100.0).pin_memory()
+    K = args.steps if args.steps is not None else 10
+    Wm = max(3, args.warmup)
+
+    def one():
+        a, b_, c = xt.to(dev, non_blocking=True), t.to(dev, non_blocking=True), x0.to(dev, non_blocking=True)
+        return tr.train_step(a, b_, c)
+    for _ in range(Wm):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ops.LAUNCHES[0] = 0
+    clocks = ClockSampler(local); clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = one()
+    lossv = float(loss)          # device -> host read of the step result
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    if rank == 0:
+        val = world * Bn * K / (ms / 1e3)
+        nparam = sum(p.numel() for p in model.parameters())
+        print(json.dumps({"metric": "training images/sec (webp_training.py step, 64^2)", "value": val, "unit": "images/s", "n_gpus": world,
+                          "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"webp_training.py training step, WebP UNet {res}x{res}, batch {Bn}/GPU, "
+                                                 "frequency_aware_loss, clip+AdamW, flat fp32 gradient all-reduce (NCCL)",
+                                     "allreduce_bytes": nparam * 4},
+                          "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 2 * xt.numel() * 4 + Bn * 4,
+                                  "d2h_bytes_per_step": 4.0 / K},
+                          "gpu_launches": ops.LAUNCHES[0], "clocks": clk, "loss": lossv}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist

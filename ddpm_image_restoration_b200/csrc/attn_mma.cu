@@ -98,7 +98,7 @@ template <int CPR> __device__ __forceinline__ int swz(int row, int chunk) {
 // is then refilled with stage t+2.
 template <int HD, int MT, int NWARPS, int EXPMODE, int SK, int MINB>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
-attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int C, float scale_log2) {
+attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int L, int C, float scale_log2) {
     constexpr int CPR = HD / 8;            // 16-byte chunks per K/V row
     constexpr int NT = NWARPS * 32;
     constexpr int ROWS = NWARPS * MT * 16;  // query rows per CTA
@@ -328,6 +328,11 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
         const float l1 = __shfl_sync(0xffffffffu, ls[mt][2], lane & ~3);
         const float i0 = 1.f / l0, i1 = 1.f / l1;
         const int ra = row0 + mt * 16 + r_lo, rb = ra + 8;
+        if (lse && (lane & 3) == 0) {   // natural-log log-sum-exp of the scaled scores (training backward)
+            float* lp = lse + ((long long)b * gridDim.y + h) * L;
+            if (ra < L) lp[ra] = (mrow[mt][0] + log2f(l0)) * 0.69314718055994531f;
+            if (rb < L) lp[rb] = (mrow[mt][1] + log2f(l1)) * 0.69314718055994531f;
+        }
         bf16* oa = out + ((long long)b * L + ra) * C + (long long)h * HD + c_lo;
         bf16* ob = out + ((long long)b * L + rb) * C + (long long)h * HD + c_lo;
 #pragma unroll
@@ -339,7 +344,7 @@ attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int
 }
 
 template <int HD, int MT, int NWARPS, int EXPMODE, int SK, int MINB>
-int launch_sk(const void* qkv, void* out, int B, int L, int C, int heads, cudaStream_t st) {
+int launch_sk(const void* qkv, void* out, float* lse, int B, int L, int C, int heads, cudaStream_t st) {
     constexpr int ROWS = NWARPS * MT * 16;
     const size_t smem = (size_t)3 * 2 * SK * HD * sizeof(bf16);
     auto kern = attn_mma_kernel<HD, MT, NWARPS, EXPMODE, SK, MINB>;
@@ -349,18 +354,18 @@ int launch_sk(const void* qkv, void* out, int B, int L, int C, int heads, cudaSt
     }
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
     dim3 grid(ceil_div(L, ROWS), heads, B);
-    kern<<<grid, NWARPS * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, L, C, scale_log2);
+    kern<<<grid, NWARPS * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, L, C, scale_log2);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
 
 // stage size: as many keys as fit the budget and divide L (fewer block barriers per key), 64 otherwise
 template <int HD, int MT, int NWARPS, int EXPMODE>
-int launch(const void* qkv, void* out, int B, int L, int C, int heads, cudaStream_t st) {
+int launch(const void* qkv, void* out, float* lse, int B, int L, int C, int heads, cudaStream_t st) {
     constexpr int SKMAX = HD <= 16 ? 256 : (HD == 32 ? 128 : 64);
     constexpr int MINB = (HD <= 16 && MT == 1) ? 4 : 1;
-    if (SKMAX > 64 && L % SKMAX == 0) return launch_sk<HD, MT, NWARPS, EXPMODE, SKMAX, MINB>(qkv, out, B, L, C, heads, st);
-    return launch_sk<HD, MT, NWARPS, EXPMODE, 64, MINB>(qkv, out, B, L, C, heads, st);
+    if (SKMAX > 64 && L % SKMAX == 0) return launch_sk<HD, MT, NWARPS, EXPMODE, SKMAX, MINB>(qkv, out, lse, B, L, C, heads, st);
+    return launch_sk<HD, MT, NWARPS, EXPMODE, 64, MINB>(qkv, out, lse, B, L, C, heads, st);
 }
 
 int g_expmode = -1;   // -1 = auto: mode 3 (25 % of the exps on the FMA pipe) at head_dim 8, mode 0 otherwise (measured on B200)
@@ -380,14 +385,14 @@ extern "C" int ddpmir_attention_set_expmode(int mode) {
 
 int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, cudaStream_t st);
 
-int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, cudaStream_t st) {
+int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, float* lse, cudaStream_t st) {
     const int hd = C / heads;
     if (L % KT != 0) return DDPMIR_ERR_UNSUPPORTED;
     const int em = g_expmode >= 0 ? g_expmode : (hd == 8 ? 3 : 0);
-#define GO(HD, MT, NW) (em == 1 ? launch<HD, MT, NW, 1>(qkv, out, B, L, C, heads, st) : \
-                        em == 2 ? launch<HD, MT, NW, 2>(qkv, out, B, L, C, heads, st) : \
-                        em == 3 ? launch<HD, MT, NW, 3>(qkv, out, B, L, C, heads, st) : \
-                        em == 4 ? launch<HD, MT, NW, 4>(qkv, out, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, B, L, C, heads, st))
+#define GO(HD, MT, NW) (em == 1 ? launch<HD, MT, NW, 1>(qkv, out, lse, B, L, C, heads, st) : \
+                        em == 2 ? launch<HD, MT, NW, 2>(qkv, out, lse, B, L, C, heads, st) : \
+                        em == 3 ? launch<HD, MT, NW, 3>(qkv, out, lse, B, L, C, heads, st) : \
+                        em == 4 ? launch<HD, MT, NW, 4>(qkv, out, lse, B, L, C, heads, st) : launch<HD, MT, NW, 0>(qkv, out, lse, B, L, C, heads, st))
     switch (hd) {
         case 8: return g_mt == 2 ? GO(8, 2, 8) : GO(8, 1, 8);
         case 16: return g_mt == 2 ? GO(16, 2, 8) : GO(16, 1, 8);
@@ -406,7 +411,7 @@ extern "C" int ddpmir_attention(const void* qkv, int dtype, int B, int L, int C,
     DDPMIR_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DDPMIR_BF16 && impl != DDPMIR_IMPL_SIMT) {
-        int rc = ddpmir_attention_mma(qkv, B, L, C, heads, out, st);
+        int rc = ddpmir_attention_mma(qkv, B, L, C, heads, out, nullptr, st);
         if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
         if (impl == DDPMIR_IMPL_TENSOR) {
             ddpmir_set_error("attention: tensor-core kernel needs L %% 64 == 0 and head_dim in {8,16,32,64,128}");

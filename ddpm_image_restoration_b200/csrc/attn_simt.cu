@@ -274,6 +274,8 @@ int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int h
     return dispatch<bf16>(qkv, out, nullptr, B, L, C, heads, st);
 }
 
+int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, float* lse, cudaStream_t st);
+
 // training forward: same kernel, also writes the per-row log-sum-exp [B, heads, L] the backward needs
 extern "C" int ddpmir_attention_train_forward(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float* lse,
                                               ddpmir_stream_t stream) {
@@ -281,6 +283,8 @@ extern "C" int ddpmir_attention_train_forward(const void* qkv, int dtype, int B,
     DDPMIR_CHECK_ARG(B > 0 && L > 0 && heads > 0 && C % heads == 0 && (C / heads) % 8 == 0, "attention_train_forward: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DDPMIR_F32) return dispatch<float>(qkv, out, lse, B, L, C, heads, st);
+    const int rc = ddpmir_attention_mma(qkv, B, L, C, heads, out, lse, st);     // tensor-core kernel when the shape fits
+    if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
     return dispatch<bf16>(qkv, out, lse, B, L, C, heads, st);
 }
 

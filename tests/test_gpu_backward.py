@@ -145,6 +145,23 @@ def test_attention_backward(T, hd, heads, L):
     assert rel(dqkv.cpu(), qkv.grad) < 2e-5
 
 
+@pytest.mark.parametrize("hd,heads,L", [(16, 4, 256), (8, 8, 128), (32, 4, 64)])
+def test_attention_train_forward_bf16_lse(T, hd, heads, L):
+    """bf16 training forward (tensor-core kernel) returns the log-sum-exp the backward needs; bf16 backward is consistent."""
+    C = hd * heads
+    qkv = bf16_round(rnd(2, L, 3 * C, seed=hd + L)).requires_grad_()
+    q, k, v = qkv.view(2, L, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(2, L, C)
+    do = rnd(2, L, C, seed=7)
+    o.backward(do)
+    out, lse = T.attention_train_forward(qkv.detach().to(torch.bfloat16).cuda(), heads)
+    assert rel(lse.cpu(), torch.logsumexp(s.detach(), -1)) < 2e-3
+    assert rel(out.float().cpu(), o.detach()) < 6e-3
+    dqkv = T.attention_backward(qkv.detach().to(torch.bfloat16).cuda(), out, do.cuda(), lse, heads)
+    assert rel(dqkv.cpu(), qkv.grad) < 1e-2
+
+
 def test_small_layers_backward(ops, T):
     # row-wise linear + SiLU (time embedding MLP)
     x = rnd(4, 256, seed=1).requires_grad_()
