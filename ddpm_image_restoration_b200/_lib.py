@@ -67,7 +67,7 @@ _SIGNATURES = {
     "ddpmir_maxpool2_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_upsample2_concat_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_attention_train_forward": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
-    "ddpmir_attention_backward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_attention_backward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_act_forward": (c_int, [_P, c_int, _P, c_int64, _P]),
     "ddpmir_act_backward": (c_int, [_P, _P, c_int, _P, c_int64, _P]),
     "ddpmir_linear_rows_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),

@@ -289,11 +289,21 @@ extern "C" int ddpmir_attention_train_forward(const void* qkv, int dtype, int B,
 }
 
 // dqkv [B, L, 3C] fp32 from qkv, o (forward output), dout [B, L, C] fp32 and lse; delta: workspace [B, heads, L] fp32
-extern "C" int ddpmir_attention_backward(const void* qkv, const void* o, int dtype, const float* dout, const float* lse,
-                                         float* delta, float* dqkv, int B, int L, int C, int heads, ddpmir_stream_t stream) {
+int ddpmir_attention_backward_mma(const void* qkv, const void* dout_bf16, const float* lse, const float* delta, float* dqkv, int B,
+                                  int L, int C, int heads, cudaStream_t st);
+
+extern "C" int ddpmir_attention_backward(const void* qkv, const void* o, int dtype, const float* dout, const void* dout_op,
+                                         const float* lse, float* delta, float* dqkv, int B, int L, int C, int heads,
+                                         ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(qkv && o && dout && lse && delta && dqkv, "attention_backward: null pointer");
     DDPMIR_CHECK_ARG(B > 0 && B <= 65535 && L > 0 && heads > 0 && C % heads == 0 && (C / heads) % 8 == 0, "attention_backward: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DDPMIR_BF16 && dout_op) {
+        // tensor-core path: delta from the fp32 gradient, the matrix products on bf16 operands
+        attn_delta_kernel<bf16><<<dim3(ceil_div((long long)heads * L, 256), B), 256, 0, st>>>((const bf16*)o, dout, delta, L, C, heads);
+        const int rc = ddpmir_attention_backward_mma(qkv, dout_op, lse, delta, dqkv, B, L, C, heads, st);
+        if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
+    }
     if (dtype == DDPMIR_F32) return dispatch_bwd<float>(qkv, o, dout, lse, delta, dqkv, B, L, C, heads, st);
     return dispatch_bwd<bf16>(qkv, o, dout, lse, delta, dqkv, B, L, C, heads, st);
 }

@@ -105,8 +105,12 @@ def attention_backward(qkv, o, dout, lse, heads):
     C = C3 // 3
     dqkv = torch.empty((B, L, C3), dtype=F32, device=qkv.device)
     delta = torch.empty((B, heads, L), dtype=F32, device=qkv.device)
-    _lib.check(_lib.lib().ddpmir_attention_backward(_p(qkv), _p(o), _code(qkv.dtype), _p(_f32(dout, "dout")), _p(lse), _p(delta),
-                                                    _p(dqkv), B, L, C, heads, _stream()), "attention_backward")
+    dout_op = None
+    if qkv.dtype == torch.bfloat16 and L % 64 == 0 and (C // heads) <= 64:
+        from .ops import cast_bf16
+        dout_op = cast_bf16(dout.contiguous())
+    _lib.check(_lib.lib().ddpmir_attention_backward(_p(qkv), _p(o), _code(qkv.dtype), _p(_f32(dout, "dout")), _p(dout_op), _p(lse),
+                                                    _p(delta), _p(dqkv), B, L, C, heads, _stream()), "attention_backward")
     LAUNCHES[0] += 3
     return dqkv
 

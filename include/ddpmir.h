@@ -297,11 +297,13 @@ int ddpmir_upsample2_concat_backward(const float* dy, float* dlo, float* dskip, 
                                      ddpmir_stream_t stream);
 
 /* Attention for training: forward that also returns the row log-sum-exp lse [B, heads, L], and the backward
- * dqkv [B, L, 3C] fp32 from (qkv, o, dout, lse); delta is a [B, heads, L] fp32 workspace. */
+ * dqkv [B, L, 3C] fp32 from (qkv, o, dout, lse); delta is a [B, heads, L] fp32 workspace.  dout_op (optional): dout
+ * cast to the operand dtype -- with bf16 operands, L % 64 == 0 and head_dim <= 64 the backward then runs on the tensor
+ * cores (attn_bwd_mma.cu); otherwise the generic fp32-FMA kernels are used. */
 int ddpmir_attention_train_forward(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float* lse,
                                    ddpmir_stream_t stream);
-int ddpmir_attention_backward(const void* qkv, const void* o, int dtype, const float* dout, const float* lse, float* delta,
-                              float* dqkv, int B, int L, int C, int heads, ddpmir_stream_t stream);
+int ddpmir_attention_backward(const void* qkv, const void* o, int dtype, const float* dout, const void* dout_op,
+                              const float* lse, float* delta, float* dqkv, int B, int L, int C, int heads, ddpmir_stream_t stream);
 
 /* Small fp32 layers: element-wise activation forward / backward (u = pre-activation), row-wise linear backward
  * (dx may be NULL; dw, db accumulated), the 3-channel input convolution (weight gradient in OIHW + the gradients of the

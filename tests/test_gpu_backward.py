@@ -145,7 +145,7 @@ def test_attention_backward(T, hd, heads, L):
     assert rel(dqkv.cpu(), qkv.grad) < 2e-5
 
 
-@pytest.mark.parametrize("hd,heads,L", [(16, 4, 256), (8, 8, 128), (32, 4, 64)])
+@pytest.mark.parametrize("hd,heads,L", [(16, 4, 256), (8, 8, 128), (32, 4, 64), (64, 4, 192), (16, 4, 1024), (128, 2, 64), (16, 2, 96)])
 def test_attention_train_forward_bf16_lse(T, hd, heads, L):
     """bf16 training forward (tensor-core kernel) returns the log-sum-exp the backward needs; bf16 backward is consistent."""
     C = hd * heads
