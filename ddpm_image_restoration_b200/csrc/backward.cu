@@ -308,12 +308,20 @@ inline int grid_for(long long total, int block) {
 
 }  // namespace
 
+int ddpmir_wgrad_mma(const void* dy, const void* x, float* out, int B, int H, int W, int Cin, int N, int taps, int n_begin, int n_count,
+                     int k_begin, int k_count, int out_ld, int oihw, cudaStream_t st);
+
 extern "C" int ddpmir_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, float* out, int B, int H, int W, int Cin,
                             int N, int taps, int n_begin, int n_count, int k_begin, int k_count, int out_ld, int oihw,
                             ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(dy && x && out, "wgrad: null pointer");
     DDPMIR_CHECK_ARG((taps == 1 || taps == 9) && n_count > 0 && k_count > 0 && n_begin >= 0 && k_begin >= 0 &&
                      n_begin + n_count <= N && k_begin + k_count <= taps * Cin, "wgrad: bad sub-block");
+    if (dy_dtype == DDPMIR_BF16 && x_dtype == DDPMIR_BF16) {      // tensor-core kernel when both operands are bf16
+        const int rc = ddpmir_wgrad_mma(dy, x, out, B, H, W, Cin, N, taps, n_begin, n_count, k_begin, k_count, out_ld, oihw,
+                                        (cudaStream_t)stream);
+        if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
+    }
     const long long M = (long long)B * H * W;
     const int tiles = ceil_div(k_count, 64) * ceil_div(n_count, 64);
     int splits = (148 * 4 + tiles - 1) / tiles;

@@ -232,41 +232,46 @@ class Trainer:
         f = f"{p}.freq_guide"
         op = lambda z: self._op(z, dt)
         Bn, H, Wd, _ = dout.shape
-        # out = conv_out(e) + sc
+        # out = conv_out(e) + sc.  Every gradient that feeds a GEMM is cast ONCE to the operand dtype (bf16 in production)
+        # and that copy serves both the data-gradient GEMM and the tensor-core weight-gradient kernel.
         dout_op = op(dout)
-        T.wgrad(dout, tp["e"], G[f"{f}.conv_out.weight"], 9, oihw=True)
+        T.wgrad(dout_op, tp["e"], G[f"{f}.conv_out.weight"], 9, oihw=True)
         T.colsum(dout, G[f"{f}.conv_out.bias"])
         de = ops.conv3x3(dout_op, W["fo_t"], co, impl, out_dtype=F32)
         # e = h3 + g*s*d
         dz, dd = T.gate_backward(de, tp["g"], tp["d"], boost, bs, low)
         dz_op = op(dz)
-        T.wgrad(dz, tp["g1"], G[f"{f}.low_freq_attn.2.weight"], 1, k_begin=0, k_count=co // 2, out_ld=co // 2)
-        T.wgrad(dz, tp["g1"], G[f"{f}.high_freq_attn.2.weight"], 1, k_begin=co // 2, k_count=co // 2, out_ld=co // 2)
+        T.wgrad(dz_op, tp["g1"], G[f"{f}.low_freq_attn.2.weight"], 1, k_begin=0, k_count=co // 2, out_ld=co // 2)
+        T.wgrad(dz_op, tp["g1"], G[f"{f}.high_freq_attn.2.weight"], 1, k_begin=co // 2, k_count=co // 2, out_ld=co // 2)
         T.colsum(dz, G[f"{f}.low_freq_attn.2.bias"], cls=1, bs=bs, low=low)
         T.colsum(dz, G[f"{f}.high_freq_attn.2.bias"], cls=0, bs=bs, low=low)
         dg1 = ops.gemm(dz_op, W["g2_t"], co, impl, out_dtype=F32)
         dpre = T.lrelu_mask_backward(dg1, tp["g1"], bs, low)
-        T.wgrad(dpre, tp["d"], G[f"{f}.low_freq_attn.0.weight"], 1, n_begin=0, n_count=co // 2)
-        T.wgrad(dpre, tp["d"], G[f"{f}.high_freq_attn.0.weight"], 1, n_begin=co // 2, n_count=co // 2)
+        dpre_op = op(dpre)
+        T.wgrad(dpre_op, tp["d"], G[f"{f}.low_freq_attn.0.weight"], 1, n_begin=0, n_count=co // 2)
+        T.wgrad(dpre_op, tp["d"], G[f"{f}.high_freq_attn.0.weight"], 1, n_begin=co // 2, n_count=co // 2)
         T.colsum(dpre, G[f"{f}.low_freq_attn.0.bias"], n_begin=0, n_count=co // 2)
         T.colsum(dpre, G[f"{f}.high_freq_attn.0.bias"], n_begin=co // 2, n_count=co // 2)
-        dd = ops.gemm(op(dpre), W["g1_t"], co, impl, out_dtype=F32, res=dd)
+        dd = ops.gemm(dpre_op, W["g1_t"], co, impl, out_dtype=F32, res=dd)
         # h3 receives de directly and through d = DCT(h3)
         Dt = sd[f"{f}.dct.dct_matrix"].t().contiguous()
         dh3 = ops.lincomb(de, 1.0, ops.block_transform(dd, Dt, 0.0, 1.0), 1.0)
         # h3 = out_proj(ao) + h2
-        T.wgrad(dh3, tp["ao"], G[f"{p}.attn.out_proj.weight"], 1)
+        dh3_op = op(dh3)
+        T.wgrad(dh3_op, tp["ao"], G[f"{p}.attn.out_proj.weight"], 1)
         T.colsum(dh3, G[f"{p}.attn.out_proj.bias"])
-        dao = ops.gemm(op(dh3), W["out_t"], co, impl, out_dtype=F32)
+        dao = ops.gemm(dh3_op, W["out_t"], co, impl, out_dtype=F32)
         dqkv = T.attention_backward(tp["qkv"].view(Bn, H * Wd, 3 * co), tp["ao"].view(Bn, H * Wd, co), dao.view(Bn, H * Wd, co),
                                     tp["lse"], fam["heads"]).view(Bn, H, Wd, 3 * co)
-        T.wgrad(dqkv, tp["h2_op"], G[f"{p}.attn.in_proj_weight"], 1)
+        dqkv_op = op(dqkv)
+        T.wgrad(dqkv_op, tp["h2_op"], G[f"{p}.attn.in_proj_weight"], 1)
         T.colsum(dqkv, G[f"{p}.attn.in_proj_bias"])
-        dh2 = ops.gemm(op(dqkv), W["in_t"], co, impl, out_dtype=F32, res=dh3)
+        dh2 = ops.gemm(dqkv_op, W["in_t"], co, impl, out_dtype=F32, res=dh3)
         # h2 = conv2(dropout(gelu(gn2(h1))))
-        T.wgrad(dh2, tp["a2d"], G[f"{p}.conv2.weight"], 9, oihw=True)
+        dh2_op = op(dh2)
+        T.wgrad(dh2_op, tp["a2d"], G[f"{p}.conv2.weight"], 9, oihw=True)
         T.colsum(dh2, G[f"{p}.conv2.bias"])
-        da2 = ops.conv3x3(op(dh2), W["conv2_t"], co, impl, out_dtype=F32)
+        da2 = ops.conv3x3(dh2_op, W["conv2_t"], co, impl, out_dtype=F32)
         if p_drop > 0:
             da2 = T.dropout(da2, p_drop, tp["dseed"])
         dh1 = T.groupnorm_backward(tp["h1"], da2, tp["st2"], sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ops.ACT_GELU,
@@ -284,10 +289,11 @@ class Trainer:
             T.colsum(dout, G[f"{p}.shortcut.bias"])
             return None
         ci = tp["x"].shape[-1]
-        T.wgrad(dh1, tp["a"], G[f"{p}.conv1.weight"], 9, oihw=True)
-        da = ops.conv3x3(op(dh1), W["conv1_t"], ci, impl, out_dtype=F32)
+        dh1_op = op(dh1)
+        T.wgrad(dh1_op, tp["a"], G[f"{p}.conv1.weight"], 9, oihw=True)
+        da = ops.conv3x3(dh1_op, W["conv1_t"], ci, impl, out_dtype=F32)
         if "sc" in W:
-            T.wgrad(dout, tp["x_op"], G[f"{p}.shortcut.weight"], 1)
+            T.wgrad(dout_op, tp["x_op"], G[f"{p}.shortcut.weight"], 1)
             T.colsum(dout, G[f"{p}.shortcut.bias"])
             dx = ops.gemm(dout_op, W["sc_t"], ci, impl, out_dtype=F32)
         else:

@@ -60,6 +60,28 @@ def test_wgrad_colsum_and_dgrad(ops, T, shape):
         assert rel(nchw(dx), x.grad) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 128, 16, 16, 9), (1, 128, 64, 8, 8, 9), (2, 64, 192, 16, 16, 1), (3, 256, 256, 4, 4, 9),
+                                   (2, 128, 128, 8, 8, 1), (1, 1024, 512, 2, 2, 9)])
+def test_wgrad_tensor_core(T, shape):
+    """bf16 operands -> mma.sync kernel; against autograd on the same bf16-rounded operands, incl. the gate sub-blocks."""
+    B, Ci, Co, H, W, taps = shape
+    ks = 3 if taps == 9 else 1
+    x = bf16_round(rnd(B, Ci, H, W, seed=1))
+    dy = bf16_round(rnd(B, Co, H, W, seed=4))
+    w = torch.zeros(Co, Ci, ks, ks, requires_grad=True)
+    F.conv2d(x, w, None, padding=ks // 2).backward(dy)
+    BF = torch.bfloat16
+    dw = torch.zeros(Co, Ci, ks, ks).cuda()
+    T.wgrad(nhwc(dy, BF), nhwc(x, BF), dw, taps, oihw=(taps == 9))
+    assert rel(dw.cpu(), w.grad) < 2e-5
+    if taps == 1:
+        lo = torch.zeros(Co, Ci // 2).cuda(); hi = torch.zeros(Co // 2, Ci).cuda()
+        T.wgrad(nhwc(dy, BF), nhwc(x, BF), lo, 1, k_begin=Ci // 2, k_count=Ci // 2, out_ld=Ci // 2)
+        T.wgrad(nhwc(dy, BF), nhwc(x, BF), hi, 1, n_begin=Co // 2, n_count=Co // 2)
+        g2 = w.grad.reshape(Co, Ci)
+        assert rel(lo.cpu(), g2[:, Ci // 2:]) < 2e-5 and rel(hi.cpu(), g2[Co // 2:]) < 2e-5
+
+
 def test_colsum_class_split(T):
     B, N, H, W = 2, 32, 8, 12
     dy = rnd(B, N, H, W, seed=1)
