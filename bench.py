@@ -286,7 +286,10 @@ def main():
         st = sampler.begin(y_dev, q, steps=traj)
         i = traj - 1
         for _ in range(warm):
-            sampler.step(st, i); i = (i - 1) % traj
+            # the e2e arm starts a fresh trajectory inside the timed region: nothing may be pre-enqueued for it
+            sampler.step(st, i, prefetch=not host_io); i = (i - 1) % traj
+        if host_io:
+            i = traj - 1
         barrier()
         ops.LAUNCHES[0] = 0
         st["h2d"] = st["d2h"] = 0; st["codec_s"] = 0.0
@@ -296,9 +299,10 @@ def main():
         t0 = time.perf_counter()
         e0.record()
         if host_io:
-            st["x_t"] = y_host.to(dev, non_blocking=True); st["h2d"] += y_host.numel() * 4
-        for _ in range(n_steps):
-            sampler.step(st, i); i = (i - 1) % traj
+            st = sampler.begin(y_host.to(dev, non_blocking=True), q, steps=traj)   # the user-facing call starts from host images
+            st["h2d"] += y_host.numel() * 4
+        for n in range(n_steps):
+            sampler.step(st, i, prefetch=not (host_io and n == n_steps - 1)); i = (i - 1) % traj
         if host_io:
             out_host = torch.empty(y_host.shape, dtype=torch.float32, pin_memory=True)
             out_host.copy_(st["x_t"], non_blocking=True); st["d2h"] += y_host.numel() * 4

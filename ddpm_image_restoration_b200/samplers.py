@@ -56,8 +56,8 @@ class _DDRMSampler:
         B, C, H, W = x_t.shape
         chunks = self._chunks(B)
         use_phase = quality < cfg["q_thr"]
-        st = dict(cfg=cfg, x_t=x_t, y=x_t.clone(), quality=quality, steps=steps, eta=eta, eta_b=eta_b, chunks=chunks,
-                  use_phase=use_phase, h2d=0, d2h=0, codec_s=0.0,
+        st = dict(cfg=cfg, x_t=x_t, x_alt=torch.empty_like(x_t), y=x_t.clone(), quality=quality, steps=steps, eta=eta, eta_b=eta_b,
+                  chunks=chunks, use_phase=use_phase, h2d=0, d2h=0, codec_s=0.0, pending=[None] * len(chunks),
                   phasor=ops.phase_reference(x_t) if (use_phase and steps > cfg["period"]) else None)
         # staging: device uint8 buffers and pinned host buffers, one set per micro-batch
         mk = lambda s, e, **kw: torch.empty((e - s, H, W, C), dtype=torch.uint8, **kw)
@@ -68,26 +68,31 @@ class _DDRMSampler:
         st["events"] = [torch.cuda.Event() for _ in chunks]
         return st
 
-    def step(self, st, i):
-        """One sampler timestep i (steps-1 ... 0) over the whole batch: webp_inference.py:566-600."""
+    def _enqueue_unet(self, st, k, i):
+        """GPU work of micro-batch k at timestep i: UNet forward, uint8 quantisation, asynchronous D2H, event."""
+        s, e = st["chunks"][k]
+        x = st["x_t"][s:e]
+        t = torch.full((e - s,), float(i) / st["steps"], dtype=torch.float32, device=x.device)
+        x_theta = self.model(x, t, t)
+        ops.quantize_u8_hwc(x_theta, out=st["dev_u8"][k])
+        st["pin_src"][k].copy_(st["dev_u8"][k], non_blocking=True)
+        st["events"][k].record()
+        st["d2h"] += st["dev_u8"][k].numel()
+        st["pending"][k] = (x_theta, t, i)
+
+    def step(self, st, i, prefetch=True):
+        """One sampler timestep i (steps-1 ... 0) over the whole batch: webp_inference.py:566-600.
+
+        Micro-batches are independent trajectories, so the loop is software-pipelined ACROSS timesteps: as soon as
+        micro-batch k has been updated, its UNet forward for timestep i-1 is enqueued (prefetch) before the host waits for
+        the codec of micro-batch k+1 -- the GPU never idles on the host codec."""
         import time
-        cfg, x_t, y, chunks = st["cfg"], st["x_t"], st["y"], st["chunks"]
-        B, C, H, W = x_t.shape
-        dev = x_t.device
-        t_val = float(i) / st["steps"]
-        x_next = torch.empty(x_t.shape, dtype=torch.float32, device=dev)
-        thetas = []
+        cfg, y, chunks = st["cfg"], st["y"], st["chunks"]
+        B, C, H, W = st["x_t"].shape
         with torch.no_grad():
-            # phase 1: enqueue all GPU work of this timestep (UNet + quantise + D2H) per micro-batch
-            for k, (s, e) in enumerate(chunks):
-                t = torch.full((e - s,), t_val, dtype=torch.float32, device=dev)
-                x_theta = self.model(x_t[s:e], t, t)
-                ops.quantize_u8_hwc(x_theta, out=st["dev_u8"][k])
-                st["pin_src"][k].copy_(st["dev_u8"][k], non_blocking=True)
-                st["events"][k].record()
-                thetas.append((x_theta, t))
-                st["d2h"] += st["dev_u8"][k].numel()
-            # phase 2: as each micro-batch lands on the host, fan its images out to the codec pool
+            for k in range(len(chunks)):
+                if st["pending"][k] is None or st["pending"][k][2] != i:
+                    self._enqueue_unet(st, k, i)
             futures = []
             for k in range(len(chunks)):
                 st["events"][k].synchronize()
@@ -95,7 +100,8 @@ class _DDRMSampler:
                     t0 = time.perf_counter()
                 futures.append(_codec.submit_roundtrip(cfg["codec"], st["quality"], st["pin_src"][k].numpy(),
                                                        st["pin_dst"][k].numpy()))
-            # phase 3: decoded pixels back to the device, fused update
+            x_cur, x_new = st["x_t"], st["x_alt"]
+            updated = []
             for k, (s, e) in enumerate(chunks):
                 for f in futures[k]:
                     f.result()
@@ -103,19 +109,25 @@ class _DDRMSampler:
                     st["codec_s"] += time.perf_counter() - t0
                 st["dev_dec"][k].copy_(st["pin_dst"][k], non_blocking=True)
                 st["h2d"] += st["pin_dst"][k].numel()
-                x_theta, t = thetas[k]
+                x_theta, t, _ = st["pending"][k]
+                st["pending"][k] = None
                 z = None
                 if self.noise_fn is not None and i > 0:
-                    z = self.noise_fn(i, x_t)[s:e].contiguous()
+                    z = self.noise_fn(i, x_cur)[s:e].contiguous()
                 # the flat NCHW element index inside the FULL batch keys the noise (noise_offset), so the result
                 # does not depend on the micro-batch split
                 ops.ddrm_update(x_theta, st["dev_dec"][k], y[s:e], t, cfg["sigma"], st["eta"], st["eta_b"], z=z,
-                                last_step=(i == 0), seed=self.seed, step=i, out=x_next[s:e],
-                                noise_offset=s * C * H * W)
-            if i > 0 and st["use_phase"] and i % cfg["period"] == 0:
-                x_next = ops.phase_consistency_cached(x_next, st["phasor"], cfg["alpha"])
-        st["x_t"] = x_next
-        return x_next
+                                last_step=(i == 0), seed=self.seed, step=i, out=x_new[s:e], noise_offset=s * C * H * W)
+                if i > 0 and st["use_phase"] and i % cfg["period"] == 0:
+                    x_new[s:e].copy_(ops.phase_consistency_cached(x_new[s:e], st["phasor"][s * C:e * C], cfg["alpha"]))
+                updated.append(k)
+                if prefetch and i > 0:
+                    # x_new is the current state of micro-batch k from here on
+                    st["x_t"], st["x_alt"] = x_new, x_cur
+                    self._enqueue_unet(st, k, i - 1)
+                    st["x_t"], st["x_alt"] = x_cur, x_new
+        st["x_t"], st["x_alt"] = x_new, x_cur
+        return st["x_t"]
 
     def sample(self, x_t, quality, steps=100, eta=0.85, eta_b=1.0):
         st = self.begin(x_t, quality, steps, eta, eta_b)

@@ -72,3 +72,16 @@ def test_training_mode_and_cpu_raise():
             m(torch.zeros(1, 3, 32, 32).cuda(), torch.zeros(1).cuda())
     finally:
         m.eval()
+
+
+def test_unet_512_bf16_vs_check_mode():
+    """512x512 (BASELINE configs[4], L = 262 144 tokens per image): far beyond what the CPU oracle finishes in seconds, so
+    the bf16 production path is checked against the fp32 check mode of the same GPU code, which the other tests pin to the
+    oracle at <= 1e-5."""
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(1, 3, 512, 512, generator=g) * 0.5
+    t = torch.tensor([0.4])
+    m = model("webp")
+    ref = m.set_precision("fp32")(x.cuda(), t.cuda()).cpu()
+    out = m.set_precision("bf16")(x.cuda(), t.cuda()).cpu()
+    assert torch.isfinite(out).all() and rel(out, ref) < 1e-2

@@ -33,3 +33,24 @@ def test_avif_checkpoint_layout_against_reference():
     m = ns["AVIFDiffusionModel"]()
     ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert ref == W.shapes("avif")
+
+
+def test_checkpoint_round_trip_with_reference_layout(tmp_path):
+    """webp_training.py:794-805 saves {'epoch', 'model_state_dict', 'optimizer_state_dict', ...}; the loader of
+    webp_inference.py:621-627 accepts that or a raw state_dict.  Our model must read the reference's file and the reference
+    must read ours."""
+    import ddpm_image_restoration_b200 as P
+    ns = rl.load_webp()
+    ref = ns["WebPDiffusionModel"]()
+    ref.load_state_dict(W.make_state_dict("webp", 3))
+    path = tmp_path / "best_ddrm_webp_model.pth"
+    torch.save({"epoch": 7, "model_state_dict": ref.state_dict(), "val_psnr": 27.1}, path)
+    ckpt = torch.load(path, map_location="cpu")
+    ours = P.WebPDiffusionModel()
+    ours.load_state_dict(ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt)
+    for (k1, v1), (k2, v2) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    torch.save(ours.state_dict(), path)                     # raw layout, written by us
+    ref2 = ns["WebPDiffusionModel"]()
+    ref2.load_state_dict(torch.load(path, map_location="cpu"))
+    assert all(torch.equal(a, b) for a, b in zip(ref2.state_dict().values(), ours.state_dict().values()))
