@@ -212,9 +212,8 @@ attn_bwd_dkv_kernel(const T* __restrict__ qkv, const float* __restrict__ dout, c
 }
 
 template <typename T, int DPT, int G>
-void launch(const void* qkv, void* out, float* lse, int B, int L, int C, int heads, cudaStream_t st) {
+void launch(const void* qkv, void* out, float* lse, int B, int L, int C, int heads, float scale, cudaStream_t st) {
     constexpr int QPB = 128 / G;
-    const float scale = 1.f / sqrtf((float)(DPT * G));
     dim3 grid(ceil_div(L, QPB), heads, B);
     attn_simt_kernel<T, DPT, G><<<grid, 128, 0, st>>>((const T*)qkv, (T*)out, lse, L, C, heads, scale);
 }
@@ -250,15 +249,16 @@ int dispatch_bwd(const void* qkv, const void* o, const float* dout, const float*
 }
 
 template <typename T>
-int dispatch(const void* qkv, void* out, float* lse, int B, int L, int C, int heads, cudaStream_t st) {
+int dispatch(const void* qkv, void* out, float* lse, int B, int L, int C, int heads, float scale, cudaStream_t st) {
     const int hd = C / heads;
+    if (scale <= 0.f) scale = 1.f / sqrtf((float)hd);   // default: the softmax scale; otherwise the factor still owed to q
     switch (hd) {
-        case 8: launch<T, 8, 1>(qkv, out, lse, B, L, C, heads, st); break;
-        case 16: launch<T, 16, 1>(qkv, out, lse, B, L, C, heads, st); break;
-        case 32: launch<T, 16, 2>(qkv, out, lse, B, L, C, heads, st); break;
-        case 64: launch<T, 16, 4>(qkv, out, lse, B, L, C, heads, st); break;
-        case 128: launch<T, 16, 8>(qkv, out, lse, B, L, C, heads, st); break;
-        case 256: launch<T, 16, 16>(qkv, out, lse, B, L, C, heads, st); break;
+        case 8: launch<T, 8, 1>(qkv, out, lse, B, L, C, heads, scale, st); break;
+        case 16: launch<T, 16, 1>(qkv, out, lse, B, L, C, heads, scale, st); break;
+        case 32: launch<T, 16, 2>(qkv, out, lse, B, L, C, heads, scale, st); break;
+        case 64: launch<T, 16, 4>(qkv, out, lse, B, L, C, heads, scale, st); break;
+        case 128: launch<T, 16, 8>(qkv, out, lse, B, L, C, heads, scale, st); break;
+        case 256: launch<T, 16, 16>(qkv, out, lse, B, L, C, heads, scale, st); break;
         default:
             ddpmir_set_error("attention: unsupported head_dim %d", hd);
             return DDPMIR_ERR_UNSUPPORTED;
@@ -269,9 +269,9 @@ int dispatch(const void* qkv, void* out, float* lse, int B, int L, int C, int he
 
 }  // namespace
 
-int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, cudaStream_t st) {
-    if (dtype == DDPMIR_F32) return dispatch<float>(qkv, out, nullptr, B, L, C, heads, st);
-    return dispatch<bf16>(qkv, out, nullptr, B, L, C, heads, st);
+int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float qscale, cudaStream_t st) {
+    if (dtype == DDPMIR_F32) return dispatch<float>(qkv, out, nullptr, B, L, C, heads, qscale, st);
+    return dispatch<bf16>(qkv, out, nullptr, B, L, C, heads, qscale, st);
 }
 
 int ddpmir_attention_mma(const void* qkv, int B, int L, int C, int heads, void* out, float* lse, cudaStream_t st);
@@ -282,10 +282,10 @@ extern "C" int ddpmir_attention_train_forward(const void* qkv, int dtype, int B,
     DDPMIR_CHECK_ARG(qkv && out && lse, "attention_train_forward: null pointer");
     DDPMIR_CHECK_ARG(B > 0 && L > 0 && heads > 0 && C % heads == 0 && (C / heads) % 8 == 0, "attention_train_forward: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DDPMIR_F32) return dispatch<float>(qkv, out, lse, B, L, C, heads, st);
+    if (dtype == DDPMIR_F32) return dispatch<float>(qkv, out, lse, B, L, C, heads, 0.f, st);
     const int rc = ddpmir_attention_mma(qkv, B, L, C, heads, out, lse, st);     // tensor-core kernel when the shape fits
     if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
-    return dispatch<bf16>(qkv, out, lse, B, L, C, heads, st);
+    return dispatch<bf16>(qkv, out, lse, B, L, C, heads, 0.f, st);
 }
 
 // dqkv [B, L, 3C] fp32 from qkv, o (forward output), dout [B, L, C] fp32 and lse; delta: workspace [B, heads, L] fp32

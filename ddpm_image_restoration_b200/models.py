@@ -189,7 +189,13 @@ class _RestorationUNet(nn.Module):
                 if ci != co:
                     q["sc_w"] = lin(sd[f"{p}.shortcut.weight"])
             q["conv2_w"] = conv3(sd[f"{p}.conv2.weight"])
-            q["in_w"] = lin(sd[f"{p}.attn.in_proj_weight"])
+            in_w, in_b = f32(sd[f"{p}.attn.in_proj_weight"]), f32(sd[f"{p}.attn.in_proj_bias"])
+            if dt == torch.bfloat16:
+                # production path: softmax scale and log2(e) folded into the q rows (ops.attention_prescaled)
+                fold = torch.ones(3 * co, 1, device=dev)
+                fold[:co] = ops.Q_PRESCALE_LOG2E / math.sqrt(co // _FAMILY[self.family]["heads"])
+                in_w, in_b = in_w * fold, in_b * fold[:, 0]
+            q["in_w"], q["in_b"] = lin(in_w), in_b.contiguous()
             q["out_w"] = lin(sd[f"{p}.attn.out_proj.weight"])
             f = f"{p}.freq_guide"
             if self.family == "avif":
@@ -303,8 +309,11 @@ class _RestorationUNet(nn.Module):
         a = ops.groupnorm_apply(h1, st, sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ops.ACT_GELU, out_dtype=dt)
         h2, h2_op = ops.conv3x3(a, W["conv2_w"], co, impl, out_dtype=f32, out2_dtype=dt, bias=sd[f"{p}.conv2.bias"])
         Bn, H, Wd, _ = h2.shape
-        qkv = ops.gemm(h2_op, W["in_w"], 3 * co, impl, bias=sd[f"{p}.attn.in_proj_bias"])
-        ao = ops.attention(qkv.view(Bn, H * Wd, 3 * co), fam["heads"], impl).view(Bn, H, Wd, co)
+        qkv = ops.gemm(h2_op, W["in_w"], 3 * co, impl, bias=W["in_b"])
+        if dt == torch.bfloat16:
+            ao = ops.attention_prescaled(qkv.view(Bn, H * Wd, 3 * co), fam["heads"]).view(Bn, H, Wd, co)
+        else:
+            ao = ops.attention(qkv.view(Bn, H * Wd, 3 * co), fam["heads"], impl).view(Bn, H, Wd, co)
         f = f"{p}.freq_guide"
         if self.family == "avif":
             h3, h3_op = ops.gemm(ao, W["out_w"], co, impl, out_dtype=f32, out2_dtype=dt,

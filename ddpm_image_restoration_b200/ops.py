@@ -330,6 +330,25 @@ def attention(qkv, heads, impl=IMPL_AUTO):
     return out
 
 
+Q_PRESCALE_LOG2E = 1.4426950408889634   # attention_prescaled expects q * log2(e) / sqrt(head_dim)
+
+
+def attention_prescaled(qkv, heads):
+    """bf16 qkv [B, L, 3C] whose q third already carries log2(e)/sqrt(head_dim) -> [B, L, C]."""
+    B, L, C3 = qkv.shape
+    C = C3 // 3
+    if qkv.dtype != torch.bfloat16:
+        raise TypeError("attention_prescaled is the bf16 inference path")
+    out = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)
+    nbytes = _lib.lib().ddpmir_attention_prescaled_workspace(B, L, heads)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
+    launches = 3 if (C // heads in (8, 16) and L % 64 == 0) else 1   # key-norm pre-pass, bounded kernel, exact redo pass
+    with _timed("attention", (B, L, C, heads), launches):
+        _lib.check(_lib.lib().ddpmir_attention_prescaled(_p(qkv), B, L, C, heads, _p(ws), _p(out), _stream()),
+                   "attention_prescaled")
+    return out
+
+
 def block_transform(x, T, alpha=0.0, beta=1.0, out_dtype=None):
     B, H, W, C = x.shape
     bs = T.shape[-1]

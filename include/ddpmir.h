@@ -21,6 +21,7 @@
 #ifndef DDPMIR_H
 #define DDPMIR_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -220,6 +221,16 @@ int ddpmir_gemm(const void* a, int dtype, int B, int H, int W, int K, const void
  * [h*hd, (h+1)*hd)); out [B, L, C] = softmax(q k^T / sqrt(hd)) v, never materialising the L x L scores. */
 int ddpmir_attention(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, int impl,
                      ddpmir_stream_t stream);
+
+/* Same result for the inference path (bf16 only) when the q third of qkv was produced ALREADY multiplied by
+ * log2(e)/sqrt(hd) (the factor is folded into in_proj_weight/bias rows [0, C) when the weights are packed, so it
+ * costs no extra rounding).  head_dim 8/16 with L % 64 == 0 take the bounded-softmax kernel: the per-row offset of
+ * the softmax is a Cauchy-Schwarz bound fixed before the first key instead of a running maximum (see attn_mma.cu);
+ * rows whose bound is too large for fp32 are redone by the exact kernel, other shapes go to the exact kernels.
+ * workspace: ddpmir_attention_prescaled_workspace(B, L, heads) bytes of device memory, caller-owned. */
+size_t ddpmir_attention_prescaled_workspace(int B, int L, int heads);
+int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
+                               ddpmir_stream_t stream);
 
 /* Blockwise per-channel transform  out = alpha*x + beta * (T_c X T_c^T)  with zero padding to a multiple of bs
  * and crop back: DCTLayer.forward webp_inference.py:161-192 (per_channel = 0, T [bs,bs]) and

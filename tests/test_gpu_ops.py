@@ -336,6 +336,55 @@ def test_attention_tensor_core_bf16(ops, expmode, hd, heads, L):
     assert rel(out2, _attn_ref(qkv, heads)) < 4e-3
 
 
+def _prescaled(qkv, heads, gain=1.0):
+    """bf16 qkv whose q third carries log2(e)/sqrt(hd) (as the packed in_proj produces it) + the fp32 tensor it stands for."""
+    C = qkv.shape[-1] // 3
+    c = 1.4426950408889634 / math.sqrt(C // heads)
+    pre = qkv.clone()
+    pre[..., :C] *= c * gain
+    pre = bf16_round(pre)
+    ref = pre.clone()
+    ref[..., :C] /= c
+    return pre.to(torch.bfloat16), ref
+
+
+@pytest.mark.parametrize("sel", [-1, 0, 1, 2, 3, 4, 5, 8, 11])
+@pytest.mark.parametrize("hd,heads,L", [(8, 8, 1024), (16, 4, 1024), (16, 8, 64), (8, 8, 4096), (8, 4, 192), (32, 4, 256), (64, 4, 128),
+                                        (16, 4, 100), (256, 4, 64)])
+def test_attention_prescaled_bf16(ops, sel, hd, heads, L):
+    """Bounded-softmax kernel (head_dim 8/16, every exp-pipe split) and the exact kernels behind the same entry point."""
+    from ddpm_image_restoration_b200 import _lib
+    if sel > 0 and hd > 16:
+        pytest.skip("the split only exists in the bounded kernel")
+    C = hd * heads
+    pre, ref = _prescaled(torch.randn(2, L, 3 * C, generator=g(hd + L)) * 1.5, heads)
+    _lib.lib().ddpmir_attention_set_expmode(-1 if sel < 0 else ((sel + 1) << 8))
+    try:
+        out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    finally:
+        _lib.lib().ddpmir_attention_set_expmode(-1)
+    assert rel(out, _attn_ref(ref, heads)) < 6e-3
+
+
+@pytest.mark.parametrize("hd,heads", [(8, 8), (16, 4)])
+def test_attention_prescaled_large_logits_take_the_exact_kernel(ops, hd, heads):
+    """Rows whose Cauchy-Schwarz logit bound exceeds the fp32-safe window are declined by the bounded kernel and redone by
+    the online-maximum kernel."""
+    C = hd * heads
+    L = 512
+    qkv = torch.randn(2, L, 3 * C, generator=g(77)) * 1.5
+    qkv[0, 100:140, :C] *= 40.0      # CTA 0 of image 0: logit bound >> 60 -> exact kernel
+    qkv[1, 300:330, :C] *= 4.0       # bound around the limit: some heads bounded, some exact
+    qkv[1, :, C:2 * C] *= 1.7
+    pre, ref = _prescaled(qkv, heads)
+    out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    want = _attn_ref(ref, heads)
+    assert torch.isfinite(out).all()
+    assert rel(out, want) < 6e-3
+    assert rel(out[0, 100:140], want[0, 100:140]) < 1e-2
+    assert rel(out[1, 300:330], want[1, 300:330]) < 1e-2
+
+
 def test_cpu_tensor_raises(ops):
     from ddpm_image_restoration_b200._lib import DdpmirError
     with pytest.raises(DdpmirError):

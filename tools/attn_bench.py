@@ -1,4 +1,6 @@
-"""Times ddpmir_attention alone (tuning aid):  python tools/attn_bench.py [hd] [heads] [L] [B] [expmode]"""
+"""Times ddpmir_attention alone (tuning aid):  python tools/attn_bench.py [hd] [heads] [L] [B] [expmode] [pre]
+
+`pre` = 1 times ddpmir_attention_prescaled (the bounded-softmax inference path); expmode (sel + 1) << 8 picks its exp split."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,16 +12,21 @@ L = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 if len(sys.argv) > 5:
     _lib.lib().ddpmir_attention_set_expmode(int(sys.argv[5]))
+pre = len(sys.argv) > 6 and int(sys.argv[6]) == 1
+attn = ops.attention_prescaled if pre else ops.attention
 C = hd * heads
-qkv = (torch.randn(B, L, 3 * C, device="cuda") * 1.0).to(torch.bfloat16)
+qkv = torch.randn(B, L, 3 * C, device="cuda")
+if pre:
+    qkv[..., :C] *= 1.4426950408889634 / hd ** 0.5
+qkv = qkv.to(torch.bfloat16)
 for _ in range(2):
-    out = ops.attention(qkv, heads)
+    out = attn(qkv, heads)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n = 3
 e0.record()
 for _ in range(n):
-    out = ops.attention(qkv, heads)
+    out = attn(qkv, heads)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 scores = B * heads * L * L
