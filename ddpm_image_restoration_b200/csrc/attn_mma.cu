@@ -652,6 +652,7 @@ extern "C" int ddpmir_attention_set_expmode(int mode) {
 }
 
 int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float qscale, cudaStream_t st);
+int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, cudaStream_t st);
 
 static int attention_mma_scaled(const void* qkv, int B, int L, int C, int heads, void* out, float* lse, float scale_log2, const int* redo,
                                 bool force_mt1, cudaStream_t st) {
@@ -719,7 +720,10 @@ extern "C" int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, 
         const int sel = g_poly >= 0 ? g_poly : 2;   // measured on B200: 2 of 8 tiles on the FMA pipe is the best split for hd 8 and 16
         const int poly = sel & 7;
         const bool rn = (sel & 8) != 0;   // +8: degree-2 polynomial
-        int rc;
+        int rc = DDPMIR_ERR_UNSUPPORTED;
+        // long sequences: tcgen05 / TMEM kernel (attn_tc.cu); +16 in the tuning hook keeps the mma.sync kernel
+        if (!(sel & 16) && L >= 1024) rc = ddpmir_attention_tc(qkv, out, kmax, flags, B, L, C, heads, sel & 15, st);
+        if (rc == DDPMIR_ERR_UNSUPPORTED) {
 #define GB(HD) (rn ? (poly == 0 ? launch_bounded<HD, 0, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \
                       poly == 1 ? launch_bounded<HD, 1, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \
                       poly == 2 ? launch_bounded<HD, 2, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \
@@ -734,6 +738,7 @@ extern "C" int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, 
                                   launch_bounded<HD, 5, 3>(qkv, out, kmax, flags, B, L, C, heads, st)))
         rc = hd == 8 ? GB(8) : GB(16);
 #undef GB
+        }
         if (rc != DDPMIR_OK) return rc;
         // exact kernel for the CTAs the bounded kernel declined (same 128-row partition)
         return attention_mma_scaled(qkv, B, L, C, heads, out, nullptr, 1.f, flags, true, st);
