@@ -7,10 +7,10 @@
 //   * one CTA = 128 query rows of one (image, head) = the 128 TMEM lanes; K/V tiles of 64 keys stream through a TMA ring;
 //   * S = Q' K^T by ONE tcgen05.mma (M128 N64 K16) per tile into TMEM (q already carries log2(e)/sqrt(hd); head_dim 8
 //     is padded to K = 16 with a zero block that the shared-memory descriptor's leading-dimension offset points at);
-//   * three softmax warpgroups, each owning two S buffers (so the next tile is waiting when the current one is done and
-//     the MMA / barrier round trip is off the critical path), read their row with tcgen05.ld (thread = row, so nothing is
-//     ever reduced across threads), evaluate P = exp2(s') -- MUFU for most columns, the FMA-pipe polynomial for the rest
-//     -- and write P as packed bf16 over the S columns they just consumed (tcgen05.st);
+//   * three softmax warpgroups, each owning two S buffers and one P buffer, read their row with tcgen05.ld (thread = row,
+//     so nothing is ever reduced across threads) and release the S buffer at once -- its refill (the tile two rounds
+//     ahead) runs under the exponentiation, so the MMA / barrier round trip is off the critical path --, evaluate
+//     P = exp2(s') -- MUFU for most columns, the FMA-pipe polynomial for the rest -- and write P as packed bf16 (tcgen05.st);
 //   * O += P V by tcgen05.mma with A = P read straight from TMEM and B = the V tile in its natural [key][dim] layout
 //     (MN-major descriptor); V is widened by a constant ones column, so the row sums of P accumulate in TMEM column
 //     head_dim for free;
@@ -79,8 +79,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
     uint64_t* kv_full = reinterpret_cast<uint64_t*>(qs + 2 * QBLK);
     uint64_t* kv_free = kv_full + NSTAGE;
     uint64_t* s_full = kv_free + NSTAGE;                    // [LAG]  QK^T of the tile in this buffer has retired
-    uint64_t* p_full = s_full + LAG;                        // [LAG]  the warpgroup has written P
-    uint64_t* q_full = p_full + LAG;
+    uint64_t* s_free = s_full + LAG;                        // [LAG]  the warpgroup has read S into registers: the buffer may be refilled
+    uint64_t* p_full = s_free + LAG;                        // [NWG]  the warpgroup has written P
+    uint64_t* p_free = p_full + NWG;                        // [NWG]  PV has consumed P
+    uint64_t* q_full = p_free + NWG;
     uint64_t* o_full = q_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
@@ -92,7 +94,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
-        for (int g = 0; g < LAG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 128); }
+        for (int g = 0; g < LAG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 128); }
+        for (int g = 0; g < NWG; ++g) { mbar_init(&p_full[g], 128); mbar_init(&p_free[g], 1); }
         mbar_init(q_full, 1);
         mbar_init(o_full, T < NWG ? T : NWG);
         fence_barrier_init();
@@ -114,7 +117,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + LAG * TK;
+    // TMEM columns: LAG S buffers of TK | NWG P buffers of TK/2 (bf16 pairs) | O
+    const uint32_t tmem_p = tmem_base + LAG * TK;
+    const uint32_t tmem_o = tmem_p + NWG * (TK / 2);
     // the PV MMAs of different tiles come from different warps in no fixed order, so all of them accumulate and the
     // accumulator (head_dim | row sum | padding) is cleared here, before the barrier below
     if (warp < 4) {
@@ -161,7 +166,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         if (lane == 0) {
             int s = 0, ph = 1;
             for (int j = 0; j < T; ++j) {
-                mbar_wait(&kv_free[s], ph);
+                mbar_wait_parked(&kv_free[s], ph, 2000);
                 unsigned char* st = stages + s * STAGE_BYTES;
                 mbar_expect_tx(&kv_full[s], 2 * KB * BLK);
 #pragma unroll
@@ -181,7 +186,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         const int g = warp - W_MMA;
         auto qk = [&](int j, int sb) {      // S(j) -> buffer sb
             const int s = j % NSTAGE;
-            mbar_wait(&kv_full[s], (j / NSTAGE) & 1);
+            mbar_wait_parked(&kv_full[s], (j / NSTAGE) & 1, 500);
             tc_fence_after();
             if (lane == 0) {
                 umma_bf16(tmem_base + sb * TK, desc_q, ((uint64_t)DESC_HI_K << 32) | (k_lo0 + s * (STAGE_BYTES >> 4)), IDESC_QK, 0u);
@@ -194,18 +199,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         int it = 0;
         for (int j = g; j < T; j += NWG, ++it) {
             const int sb = g + NWG * (it % NBUF), s = j % NSTAGE;
-            mbar_wait(&p_full[sb], (it / NBUF) & 1);
+            // the warpgroup holds S(j) in registers: refill its buffer with the tile NBUF rounds ahead while it exponentiates
+            if (j + NWG * NBUF < T) {
+                mbar_wait_parked(&s_free[sb], (it / NBUF) & 1, 500);
+                qk(j + NWG * NBUF, sb);
+            }
+            mbar_wait_parked(&p_full[g], it & 1, 500);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t v_lo = v_lo0 + s * (STAGE_BYTES >> 4);
 #pragma unroll
                 for (int ks = 0; ks < TK / 16; ++ks)
-                    umma_bf16_ts(tmem_o, tmem_base + sb * TK + ks * 8, ((uint64_t)DESC_HI_V << 32) | (v_lo + ks * 16), IDESC_PV, 1u);
-                umma_commit(&kv_free[s]);       // K and V of this stage are consumed once these MMAs retire
+                    umma_bf16_ts(tmem_o, tmem_p + g * (TK / 2) + ks * 8, ((uint64_t)DESC_HI_V << 32) | (v_lo + ks * 16), IDESC_PV, 1u);
+                umma_commit(&p_free[g]);        // P may be overwritten once these MMAs retire
+                umma_commit(&kv_free[s]);       // ... and K and V of this stage are consumed
                 if (j + NWG >= T) umma_commit(&o_full[0]);   // this warp's last tile
             }
             __syncwarp();
-            if (j + NWG * NBUF < T) qk(j + NWG * NBUF, sb);   // refill the buffer: ordered behind the PV MMAs in the tensor pipe
         }
     } else {
         // ---- softmax warpgroups: thread = query row -------------------------------------------------------------------
@@ -223,24 +233,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
                 pk[i] = pack_bf16_trunc(e0, e1);
             }
         };
+        const uint32_t p_addr = lane_base + (tmem_p - tmem_base) + g * (TK / 2);
         int it = 0;
         for (int j = g; j < T; j += NWG, ++it) {
             const int sb = g + NWG * (it % NBUF);
             const uint32_t s_addr = lane_base + sb * TK;
-            mbar_wait(&s_full[sb], (it / NBUF) & 1);
+            mbar_wait_parked(&s_full[sb], (it / NBUF) & 1, 500);
             tc_fence_after();
-            uint32_t sv[TK / 32][32], pk[16];
+            uint32_t sv[TK / 32][32], pk[TK / 32][16];
 #pragma unroll
             for (int c = 0; c < TK / 32; ++c) tmem_ld32_nowait(s_addr + c * 32, sv[c]);
             tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&s_free[sb]);                 // S is in registers: the MMA warp may refill the buffer
 #pragma unroll
-            for (int c = 0; c < TK / 32; ++c) {
-                exp_pack(sv[c], pk);
-                tmem_st16(s_addr + c * 16, pk);      // P (bf16 pairs) over S columns this thread has already consumed
+            for (int c = 0; c < TK / 32; ++c) exp_pack(sv[c], pk[c]);
+            if (it > 0) {                             // PV of the previous tile has read P
+                mbar_wait_parked(&p_free[g], (it - 1) & 1, 500);
+                tc_fence_after();
             }
+#pragma unroll
+            for (int c = 0; c < TK / 32; ++c) tmem_st16(p_addr + c * 16, pk[c]);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&p_full[sb]);
+            mbar_arrive(&p_full[g]);
         }
         if (g == 0) {
             // ---- epilogue: O / row sum -> bf16 ---------------------------------------------------------------------------
@@ -284,7 +300,7 @@ template <int HD, int POLY, int DEG>
 int launch(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, cudaStream_t st) {
     constexpr int NO = HD == 8 ? 16 : 32;
     // the kernel owns all 512 TMEM columns, so exactly one CTA may live on an SM: ask for more than half of the shared memory
-    constexpr int need = NSTAGE * (2 + NO / 8) * BLK + 2 * QBLK + (2 * NSTAGE + 2 * LAG + 2) * 8 + 16 + 128;
+    constexpr int need = NSTAGE * (2 + NO / 8) * BLK + 2 * QBLK + (2 * NSTAGE + 2 * LAG + 2 * NWG + 2) * 8 + 16 + 128;
     constexpr int smem = need > 120 * 1024 ? need : 120 * 1024;
     auto kern = attn_tc_kernel<HD, POLY, DEG>;
     static bool attr_set = false;

@@ -154,3 +154,19 @@ static __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t smem_addr, u
     d |= (uint64_t)1 << 46;
     return d;
 }
+// mbar_wait for single-role warps that wait long: the suspend-time hint lets the hardware park the warp instead of having it
+// spin through the issue slots of the warps that share its scheduler; it is woken as soon as the phase completes
+static __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(hint_ns) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
