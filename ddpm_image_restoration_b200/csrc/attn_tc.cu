@@ -25,8 +25,8 @@ namespace {
 
 constexpr int TQ = 128;                         // query rows per CTA
 constexpr int TK = 64;                          // keys per tile
-constexpr int NWG = 3;                          // softmax warpgroups
-constexpr int NBUF = 2;                         // S/P buffers per warpgroup: the next S tiles are ready before the current one is done
+constexpr int NWG = 4;                          // softmax warpgroups
+constexpr int NBUF = 1;                         // S/P buffers per warpgroup: the next S tiles are ready before the current one is done
 constexpr int LAG = NWG * NBUF;                 // S/P buffers in flight
 constexpr int NSTAGE = 10;                      // K/V ring (a stage is released by the PV of its tile)
 // single-role warps after the softmax warps.  One tcgen05.mma costs its issuing warp ~75 cycles of dependent uniform-datapath

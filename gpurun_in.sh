@@ -1,3 +1,5 @@
-timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "prescaled" 2>&1 | tail -3
-for sel in 0 2 3 4 10 11 12; do python tools/attn_bench.py 8 8 65536 4 $(( (sel+1)*256 )) 1; done
-for sel in 0 2 3 11; do python tools/attn_bench.py 16 4 65536 4 $(( (sel+1)*256 )) 1; done
+python -m pytest tests -m gpu -q 2>&1 | tail -6
+python bench.py --steps 12 --warmup 3 > gpurun_out/bench_r1_short.json 2> gpurun_out/bench_r1_short.err; python -c "
+import json
+d=json.load(open('gpurun_out/bench_r1_short.json'))
+print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e']['value'], d['roofline']['launch_ms'], d['roofline']['share_of_step'], d['roofline']['exp_pipe'])"

@@ -348,11 +348,12 @@ def _prescaled(qkv, heads, gain=1.0):
     return pre.to(torch.bfloat16), ref
 
 
-@pytest.mark.parametrize("sel", [-1, 0, 1, 2, 3, 4, 5, 8, 11])
+@pytest.mark.parametrize("sel", [-1, 0, 1, 2, 3, 4, 5, 8, 11, 12, 18, 27])
 @pytest.mark.parametrize("hd,heads,L", [(8, 8, 1024), (16, 4, 1024), (16, 8, 64), (8, 8, 4096), (8, 4, 192), (32, 4, 256), (64, 4, 128),
-                                        (16, 4, 100), (256, 4, 64)])
+                                        (16, 4, 100), (256, 4, 64), (16, 8, 2048), (8, 4, 1152)])
 def test_attention_prescaled_bf16(ops, sel, hd, heads, L):
-    """Bounded-softmax kernel (head_dim 8/16, every exp-pipe split) and the exact kernels behind the same entry point."""
+    """Bounded-softmax kernels (head_dim 8/16: tcgen05/TMEM kernel for L >= 1024 with L % 128 == 0, mma.sync kernel otherwise
+    or with +16 in the selector; every exp-pipe split) and the exact kernels behind the same entry point."""
     from ddpm_image_restoration_b200 import _lib
     if sel > 0 and hd > 16:
         pytest.skip("the split only exists in the bounded kernel")
