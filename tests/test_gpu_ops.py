@@ -386,6 +386,31 @@ def test_attention_prescaled_large_logits_take_the_exact_kernel(ops, hd, heads):
     assert rel(out[1, 300:330], want[1, 300:330]) < 1e-2
 
 
+@pytest.mark.parametrize("hd,heads", [(8, 8), (16, 4)])
+def test_attention_full_resolution_kernels_agree(ops, hd, heads):
+    """BASELINE's full size (L = 256*256 tokens): the tcgen05 bounded-softmax kernel, the mma.sync bounded-softmax kernel and the
+    exact online-maximum kernel (unscaled q) must agree; softmax rows sum to one, so a constant V must come back unchanged."""
+    from ddpm_image_restoration_b200 import _lib
+    C, L = hd * heads, 65536
+    qkv = torch.randn(1, L, 3 * C, generator=g(3)) * 1.2
+    qkv[..., 2 * C:] = 0.75                                   # constant V: out == 0.75 whatever the probabilities are
+    pre, ref = _prescaled(qkv, heads)
+    out_tc = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    assert (out_tc - 0.75).abs().max() < 4e-3
+    # random V: the three kernels against each other
+    qkv = torch.randn(1, L, 3 * C, generator=g(5)) * 1.2
+    pre, ref = _prescaled(qkv, heads)
+    out_tc = ops.attention_prescaled(pre.cuda(), heads).float()
+    _lib.lib().ddpmir_attention_set_expmode((18 + 1) << 8)    # +16: mma.sync bounded kernel
+    try:
+        out_mma = ops.attention_prescaled(pre.cuda(), heads).float()
+    finally:
+        _lib.lib().ddpmir_attention_set_expmode(-1)
+    out_exact = ops.attention(ref.to(torch.bfloat16).cuda(), heads, ops.IMPL_TENSOR).float()
+    assert rel(out_tc.cpu(), out_exact.cpu()) < 6e-3
+    assert rel(out_mma.cpu(), out_exact.cpu()) < 6e-3
+
+
 def test_cpu_tensor_raises(ops):
     from ddpm_image_restoration_b200._lib import DdpmirError
     with pytest.raises(DdpmirError):
