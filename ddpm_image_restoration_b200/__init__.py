@@ -4,13 +4,13 @@ Azure0413/DDPM_Image_Restoration (UNet forward, per-step update, data-consistenc
 Everything on the device runs through libddpmir.so (hand-written CUDA, C ABI in include/ddpmir.h); there is no
 CPU or PyTorch-op fallback.  Build with `python -m ddpm_image_restoration_b200.build`.
 """
-from .codec import avif_compress, jpeg_compress, webp_compress  # noqa: F401
+from .codec import DCTProcessor, avif_compress, jpeg_compress, webp_compress  # noqa: F401
 from .losses import color_loss, color_preservation_loss, frequency_aware_loss  # noqa: F401
 from .models import AVIFDiffusionModel, JPEGDiffusionModel, WebPDiffusionModel  # noqa: F401
 from .samplers import (DDRMAVIFSampler, DDRMJPEGSampler, DDRMWebPSampler, GaussianMixtureSampler,  # noqa: F401
                        phase_consistency, svd_structure_preservation)
 
 __all__ = ["WebPDiffusionModel", "JPEGDiffusionModel", "AVIFDiffusionModel", "DDRMWebPSampler", "DDRMJPEGSampler",
-           "DDRMAVIFSampler", "GaussianMixtureSampler", "webp_compress", "avif_compress", "jpeg_compress",
+           "DDRMAVIFSampler", "GaussianMixtureSampler", "webp_compress", "avif_compress", "jpeg_compress", "DCTProcessor",
            "phase_consistency", "svd_structure_preservation", "color_loss", "color_preservation_loss",
            "frequency_aware_loss"]

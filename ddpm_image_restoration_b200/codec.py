@@ -120,3 +120,18 @@ def avif_compress(x, quality):
 
 def jpeg_compress(x, quality):
     return _compress(x, quality, "jpeg")
+
+
+class DCTProcessor:
+    """Drop-in for DCTProcessor (experiments/code/dct.ipynb#c2:L43-139), the reference's pure-torch JPEG simulator, whose
+    scalar Python loops over every 8x8 block are replaced by one kernel (ddpmir_jpeg_dct_project).  Images are fp32 NCHW
+    on the 0..255 scale, channel 0 uses the luma table and the others the chroma table, exactly as the reference does."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DCTProcessor runs on CUDA only (no CPU fallback)")
+
+    def jpeg_compress(self, images, quality=50):
+        from . import ops
+        return ops.jpeg_dct_project(images.to(self.device).contiguous().float(), quality)

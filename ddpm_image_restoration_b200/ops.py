@@ -98,6 +98,18 @@ def ddrm_update(x_theta, codec, y, t, sigma_scale, eta=0.85, eta_b=1.0, z=None, 
     return out
 
 
+def jpeg_dct_project(x, quality, in_scale=1.0, in_offset=0.0):
+    """DCTProcessor.jpeg_compress (dct.ipynb#c2:L100-139) on fp32 NCHW images; (in_scale, in_offset) maps x to 0..255."""
+    _f32(x, "x")
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    rc = _lib.lib().ddpmir_jpeg_dct_project(_p(x), _p(out), B, C, H, W, float(quality), float(in_scale), float(in_offset),
+                                            _stream())
+    _lib.check(rc, "jpeg_dct_project")
+    LAUNCHES[0] += 1
+    return out
+
+
 def gmm_update(x_t, pred, y=None, svd_prior=None, g=0.0, z=None, use_first=True, noise_scale=0.0, last_step=False,
                seed=0, step=0):
     out = torch.empty_like(x_t)

@@ -30,11 +30,17 @@ _DDRM = {
 class _DDRMSampler:
     family = None
 
-    def __init__(self, model, seed=0, micro_batches=None, noise_fn=None):
+    def __init__(self, model, seed=0, micro_batches=None, noise_fn=None, projection="codec"):
+        """projection: "codec" = the reference's host codec round trip (Pillow, bit-identical bytes); "dct" = opt-in GPU
+        data-consistency projection in the DCT domain (DCTProcessor.jpeg_compress, dct.ipynb#c2:L100-139):
+        no host hop, NOT libjpeg -- results differ from the codec path and are checked by PSNR, not bit-exactly."""
+        if projection not in ("codec", "dct"):
+            raise ValueError(projection)
         self.model = model
         self.seed = seed
         self.micro_batches = micro_batches
         self.noise_fn = noise_fn
+        self.projection = projection
         self.last_stats = {}
 
     def _chunks(self, B):
@@ -89,6 +95,8 @@ class _DDRMSampler:
         import time
         cfg, y, chunks = st["cfg"], st["y"], st["chunks"]
         B, C, H, W = st["x_t"].shape
+        if self.projection == "dct":
+            return self._step_dct(st, i)
         with torch.no_grad():
             for k in range(len(chunks)):
                 if st["pending"][k] is None or st["pending"][k][2] != i:
@@ -126,6 +134,26 @@ class _DDRMSampler:
                     st["x_t"], st["x_alt"] = x_new, x_cur
                     self._enqueue_unet(st, k, i - 1)
                     st["x_t"], st["x_alt"] = x_cur, x_new
+        st["x_t"], st["x_alt"] = x_new, x_cur
+        return st["x_t"]
+
+    def _step_dct(self, st, i):
+        """The same timestep with the DCT-domain projection instead of the host codec: everything stays on the device."""
+        cfg, y = st["cfg"], st["y"]
+        B, C, H, W = st["x_t"].shape
+        x_cur, x_new = st["x_t"], st["x_alt"]
+        with torch.no_grad():
+            for s, e in st["chunks"]:
+                t = torch.full((e - s,), float(i) / st["steps"], dtype=torch.float32, device=x_cur.device)
+                x_theta = self.model(x_cur[s:e], t, t)
+                proj = ops.jpeg_dct_project(x_theta, st["quality"], 127.5, 127.5)
+                z = None
+                if self.noise_fn is not None and i > 0:
+                    z = self.noise_fn(i, x_cur)[s:e].contiguous()
+                ops.ddrm_update(x_theta, proj, y[s:e], t, cfg["sigma"], st["eta"], st["eta_b"], z=z, last_step=(i == 0),
+                                seed=self.seed, step=i, out=x_new[s:e], noise_offset=s * C * H * W)
+                if i > 0 and st["use_phase"] and i % cfg["period"] == 0:
+                    x_new[s:e].copy_(ops.phase_consistency_cached(x_new[s:e], st["phasor"][s * C:e * C], cfg["alpha"]))
         st["x_t"], st["x_alt"] = x_new, x_cur
         return st["x_t"]
 

@@ -232,6 +232,15 @@ size_t ddpmir_attention_prescaled_workspace(int B, int L, int heads);
 int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
                                ddpmir_stream_t stream);
 
+/* DCT-domain JPEG projection: DCTProcessor.jpeg_compress, experiments/code/dct.ipynb#c2:L100-139, the
+ * reference's pure-torch JPEG simulator: per channel and 8x8 block  c = DCT(x255 - 128);  c = round(c / Q) * Q  (luma
+ * table for channel 0, chroma table otherwise, scaled by `quality` as at L105-112);  x255' = IDCT(c) + 128.  No colour
+ * conversion and no clamping, as in the reference.  x255 = x * in_scale + in_offset and out = (x255' - in_offset) / in_scale:
+ * (1, 0) projects 0..255 images like the reference, (127.5, 127.5) projects the sampler's [-1, 1] images.  fp32 NCHW,
+ * H % 8 == 0, W % 8 == 0.  An opt-in replacement of the host codec round trip in the JPEG sampler -- NOT libjpeg. */
+int ddpmir_jpeg_dct_project(const float* x, float* out, int B, int C, int H, int W, float quality, float in_scale,
+                            float in_offset, ddpmir_stream_t stream);
+
 /* Blockwise per-channel transform  out = alpha*x + beta * (T_c X T_c^T)  with zero padding to a multiple of bs
  * and crop back: DCTLayer.forward webp_inference.py:161-192 (per_channel = 0, T [bs,bs]) and
  * AVIFAdaptiveTransform avif_inference.py:140-177 (per_channel = 1, T [C,bs,bs]).  bs in {4, 8}. T fp32. */

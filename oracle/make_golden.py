@@ -8,6 +8,7 @@ Fixtures (all small):
   ddrm_{webp,jpeg,avif}_32.npz   reference DDRM sampler, 6 steps, noise injected = oracle.restated.philox_normal
   gmm_jpeg_32.npz                reference GaussianMixtureSampler (0409), 8 steps, with SVD guide + phase consistency
   ops.npz                        codec round trips, phase_consistency, svd_structure_preservation, colour losses
+  dct_jpeg.npz                   DCTProcessor.jpeg_compress (dct.ipynb#c2) at q 10/50/90 on two 16x24 images
   traj256_webp.npz               (--trajectory256) BASELINE config 1: one 256x256 WebP q=10 image, 80 steps, computed
                                  with the restated oracle (the verbatim reference cannot allocate 68.7 GB at 256x256)
 """
@@ -149,6 +150,13 @@ def op_goldens():
     save("ops.npz", **d)
 
 
+def dct_goldens():
+    """dct_jpeg.npz: DCTProcessor.jpeg_compress (dct.ipynb#c2) on 0..255 images, run with the reference's own scalar loops."""
+    P = rl.load_dct_processor()["DCTProcessor"](torch.device("cpu"))
+    x = (W.synthetic_images(2, 16, 24, seed=99) * 127.5 + 127.5).contiguous()
+    save("dct_jpeg.npz", x=x, q10=P.jpeg_compress(x, quality=10), q50=P.jpeg_compress(x, quality=50), q90=P.jpeg_compress(x, quality=90))
+
+
 def trajectory256(n_images=1):
     fam, q, steps = "webp", 10, 80
     sd = W.make_state_dict(fam, 0)
@@ -180,6 +188,6 @@ if __name__ == "__main__":
     if args.trajectory256:
         trajectory256(args.images)
     else:
-        for fn in (op_goldens, unet_goldens, sampler_goldens):
+        for fn in (op_goldens, unet_goldens, sampler_goldens, dct_goldens):
             if not args.only or args.only in fn.__name__:
                 fn()

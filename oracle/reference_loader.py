@@ -116,3 +116,19 @@ def load_conv_deep_color_loss():
     ns = _exec(_slice(c0, [(60, 73)]), "ref_conv_deep",
                prelude="import torch\nimport torch.nn.functional as F\nfrom torch import nn\n")
     return ns
+
+
+def load_dct_processor():
+    """experiments/code/dct.ipynb cell 2 lines 43-139 (`DCTProcessor`: the pure-torch JPEG simulator with quant tables)."""
+    _install_stubs()
+    c2 = _nb_cell("experiments/code/dct.ipynb", 2)
+    # The reference calls torch.cos() on Python floats (L81, L96), which raises TypeError -- the notebook's own run stopped
+    # there.  To execute the algorithm as written, the class sees a `torch` whose cos() wraps scalars in tensors; every
+    # other attribute is the real torch.
+    prelude = ("import numpy as np\nimport torch as _torch\n"
+               "class _TorchScalarCos:\n"
+               "    def __getattr__(self, name):\n        return getattr(_torch, name)\n"
+               "    @staticmethod\n    def cos(v):\n        return _torch.cos(_torch.as_tensor(v, dtype=_torch.float64))\n"
+               "torch = _TorchScalarCos()\n")
+    ns = _exec(_slice(c2, [(43, 139)]), "ref_dct", prelude=prelude)
+    return ns

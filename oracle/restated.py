@@ -456,6 +456,43 @@ def psnr(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# DCT-domain JPEG projection: experiments/code/dct.ipynb cell 2, DCTProcessor
+# ----------------------------------------------------------------------------------------------------------
+JPEG_QUANT_Y = torch.tensor([      # dct.ipynb#c2:L47-56
+    [16, 11, 10, 16, 24, 40, 51, 61], [12, 12, 14, 19, 26, 58, 60, 55], [14, 13, 16, 24, 40, 57, 69, 56],
+    [14, 17, 22, 29, 51, 87, 80, 62], [18, 22, 37, 56, 68, 109, 103, 77], [24, 35, 55, 64, 81, 104, 113, 92],
+    [49, 64, 78, 87, 103, 121, 120, 101], [72, 92, 95, 98, 112, 100, 103, 99]], dtype=torch.float32)
+JPEG_QUANT_C = torch.tensor([      # dct.ipynb#c2:L58-67
+    [17, 18, 24, 47, 99, 99, 99, 99], [18, 21, 26, 66, 99, 99, 99, 99], [24, 26, 56, 99, 99, 99, 99, 99],
+    [47, 66, 99, 99, 99, 99, 99, 99], [99] * 8, [99] * 8, [99] * 8, [99] * 8], dtype=torch.float32)
+
+
+def jpeg_quant_tables(quality) -> Tuple[torch.Tensor, torch.Tensor]:
+    """dct.ipynb#c2:L105-112: scale = 50/q below 50, 2 - q/50 above; tables rounded and clamped to >= 1."""
+    scale = 50 / quality if quality < 50 else 2 - quality / 50
+    return (torch.clamp((JPEG_QUANT_Y * scale).round(), min=1), torch.clamp((JPEG_QUANT_C * scale).round(), min=1))
+
+
+def dct_jpeg_project(images: torch.Tensor, quality) -> torch.Tensor:
+    """DCTProcessor.jpeg_compress (dct.ipynb#c2:L100-139), vectorised: per channel and 8x8 block, orthonormal DCT-II of
+    (block - 128), round(dct / Q) * Q with the luma table for channel 0 and the chroma table for the others, inverse DCT,
+    + 128.  Images are on the 0..255 scale; no colour conversion, no clamping (as in the reference)."""
+    B, C, H, W = images.shape
+    assert H % 8 == 0 and W % 8 == 0
+    k = torch.arange(8, dtype=torch.float64)
+    D = torch.cos((2 * k[None, :] + 1) * k[:, None] * math.pi / 16) * 0.5          # D[u, x], 0.25 = 0.5 * 0.5 over both axes
+    D[0] *= 1 / math.sqrt(2)
+    D = D.to(images.dtype)
+    qy, qc = jpeg_quant_tables(quality)
+    blocks = (images - 128).reshape(B, C, H // 8, 8, W // 8, 8).permute(0, 1, 2, 4, 3, 5)      # [B,C,by,bx,8,8]
+    coef = D @ blocks @ D.T
+    q = torch.stack([qy] + [qc] * (C - 1)).to(images.dtype).view(1, C, 1, 1, 8, 8)
+    deq = torch.round(coef / q) * q
+    rec = D.T @ deq @ D + 128
+    return rec.permute(0, 1, 2, 4, 3, 5).reshape(B, C, H, W)
+
+
+# ----------------------------------------------------------------------------------------------------------
 # Philox4x32-10 known-answer reference for the in-kernel noise generator
 # ----------------------------------------------------------------------------------------------------------
 def philox4x32_10(counter: np.ndarray, key: np.ndarray) -> np.ndarray:

@@ -367,12 +367,12 @@ def test_attention_prescaled_bf16(ops, sel, hd, heads, L):
     assert rel(out, _attn_ref(ref, heads)) < 6e-3
 
 
+@pytest.mark.parametrize("L", [512, 2048])      # mma.sync bounded kernel / tcgen05 kernel
 @pytest.mark.parametrize("hd,heads", [(8, 8), (16, 4)])
-def test_attention_prescaled_large_logits_take_the_exact_kernel(ops, hd, heads):
+def test_attention_prescaled_large_logits_take_the_exact_kernel(ops, hd, heads, L):
     """Rows whose Cauchy-Schwarz logit bound exceeds the fp32-safe window are declined by the bounded kernel and redone by
     the online-maximum kernel."""
     C = hd * heads
-    L = 512
     qkv = torch.randn(2, L, 3 * C, generator=g(77)) * 1.5
     qkv[0, 100:140, :C] *= 40.0      # CTA 0 of image 0: logit bound >> 60 -> exact kernel
     qkv[1, 300:330, :C] *= 4.0       # bound around the limit: some heads bounded, some exact

@@ -134,3 +134,52 @@ def test_trajectory256_webp_psnr(golden, precision, fixture):
     print(f"traj256 {precision} ({y.shape[0]} images): PSNR {got:.4f} dB vs oracle {float(d['psnr_out']):.4f} dB; "
           f"vs oracle images {R.psnr(out, torch.from_numpy(d['out']).float()):.2f} dB")
     assert abs(got - float(d["psnr_out"])) < 0.05
+
+
+@pytest.mark.parametrize("q", [10, 50, 90])
+def test_dct_jpeg_projection_kernel(golden, q):
+    """ddpmir_jpeg_dct_project against the reference fixture (exact up to fp32 arithmetic order) and, at BASELINE's full
+    size, against the oracle: a coefficient within ~1e-5 of a rounding tie may flip, so a vanishing fraction of 8x8 blocks
+    may differ by one quantisation step; everything else agrees to fp32 rounding."""
+    import ddpm_image_restoration_b200 as P
+    d = golden("dct_jpeg.npz")
+    x = torch.from_numpy(d["x"])
+    proc = P.DCTProcessor("cuda")
+    out = proc.jpeg_compress(x.cuda(), quality=q).cpu()
+    assert (out - torch.from_numpy(d[f"q{q}"])).abs().max() < 2e-3
+    g = torch.Generator().manual_seed(q)
+    big = torch.rand(4, 3, 256, 256, generator=g) * 255
+    got, want = proc.jpeg_compress(big.cuda(), quality=q).cpu(), R.dct_jpeg_project(big, q)
+    diff = (got - want).abs()
+    blocks_off = (diff.reshape(4, 3, 32, 8, 32, 8).amax(dim=(3, 5)) > 1e-2).float().mean()
+    assert blocks_off < 1e-3 and diff.max() <= R.jpeg_quant_tables(q)[1].max()
+    assert torch.median(diff) < 1e-4
+    # the [-1, 1] form used by the sampler is the same map
+    from ddpm_image_restoration_b200 import ops
+    x11 = (big / 127.5 - 1).cuda()
+    back = ops.jpeg_dct_project(x11, q, 127.5, 127.5).cpu() * 127.5 + 127.5
+    assert torch.median((back - want).abs()) < 1e-3
+
+
+def test_ddrm_jpeg_sampler_with_gpu_dct_projection():
+    """Opt-in device-only data consistency: same trajectory as the oracle sampler run with the restated
+    DCTProcessor as its codec function, and a restoration quality comparable to the host-codec path."""
+    import ddpm_image_restoration_b200 as P
+    clean = W.synthetic_images(2, 64, 64, seed=11)
+    quality, steps = 10, 6
+    y = R.dct_jpeg_project(clean * 127.5 + 127.5, quality) / 127.5 - 1
+    sd = W.make_state_dict("jpeg", 0)
+    model_fn = lambda x, t, lvl: R.unet_forward(sd, x, t, lvl, "jpeg")
+    codec_fn = lambda z, q: R.dct_jpeg_project(z * 127.5 + 127.5, q) / 127.5 - 1
+    want = R.ddrm_sample(model_fn, y, quality, steps, "jpeg", philox_noise, codec_fn=codec_fn)
+    m = load_model("jpeg").set_precision("fp32")
+    out = P.DDRMJPEGSampler(m, noise_fn=philox_noise, projection="dct").sample(y.cuda(), quality, steps=steps).cpu()
+    assert abs(R.psnr(out, clean) - R.psnr(want, clean)) < 0.05
+    # at q = 10 one flipped rounding decision moves a coefficient by up to 495 (the chroma table's largest step), and six
+    # steps of a random-init network amplify it: the trajectories agree closely in most 8x8 blocks, not in all of them
+    assert torch.median((out - want).abs()) < 5e-3 and R.psnr(out, want) > 25.0
+    m.set_precision("bf16")
+    out_bf = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="dct").sample(y.cuda(), quality, steps=steps).cpu()
+    assert abs(R.psnr(out_bf, clean) - R.psnr(want, clean)) < 0.4
+    with pytest.raises(ValueError):
+        P.DDRMJPEGSampler(m, projection="libjpeg")

@@ -116,3 +116,18 @@ def test_trajectory256_fixture_is_consistent(golden):
     assert d["out"].shape == (1, 3, 256, 256) and int(d["steps"]) == 80 and int(d["quality"]) == 10
     clean = torch.from_numpy(d["clean_u8"]).float() / 255 * 2 - 1
     assert abs(R.psnr(torch.from_numpy(d["out"]).float(), clean) - float(d["psnr_out"])) < 0.01
+
+
+def test_dct_jpeg_projection_vs_reference_fixture(golden):
+    """DCTProcessor.jpeg_compress (dct.ipynb#c2:L100-139), run with the reference's own scalar loops -> dct_jpeg.npz."""
+    d = golden("dct_jpeg.npz")
+    x = torch.from_numpy(d["x"])
+    for q in (10, 50, 90):
+        out = R.dct_jpeg_project(x, q)
+        assert (out - torch.from_numpy(d[f"q{q}"])).abs().max() < 1e-3      # 0..255 scale
+    # quality scaling of the tables (L105-112)
+    qy, qc = R.jpeg_quant_tables(10)
+    assert qy[0, 0] == 80 and qc[7, 7] == 495 and R.jpeg_quant_tables(100)[0].max() == 1
+    # projection: applying it twice changes nothing beyond rounding
+    once = R.dct_jpeg_project(x, 50)
+    assert (R.dct_jpeg_project(once, 50) - once).abs().max() < 1e-3

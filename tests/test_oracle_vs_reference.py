@@ -54,3 +54,13 @@ def test_checkpoint_round_trip_with_reference_layout(tmp_path):
     ref2 = ns["WebPDiffusionModel"]()
     ref2.load_state_dict(torch.load(path, map_location="cpu"))
     assert all(torch.equal(a, b) for a, b in zip(ref2.state_dict().values(), ours.state_dict().values()))
+
+
+def test_dct_processor_against_reference():
+    """experiments/code/dct.ipynb cell 2: the reference's scalar-loop JPEG simulator (its torch.cos(float) calls need the
+    loader's scalar shim to run at all) against the vectorised restatement."""
+    P = rl.load_dct_processor()["DCTProcessor"](torch.device("cpu"))
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 3, 8, 16, generator=g) * 255
+    for q in (5, 50, 95):
+        assert (P.jpeg_compress(x, quality=q) - R.dct_jpeg_project(x, q)).abs().max() < 1e-3
