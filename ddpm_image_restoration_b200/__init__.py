@@ -5,6 +5,7 @@ Everything on the device runs through libddpmir.so (hand-written CUDA, C ABI in 
 CPU or PyTorch-op fallback.  Build with `python -m ddpm_image_restoration_b200.build`.
 """
 from .codec import DCTProcessor, avif_compress, jpeg_compress, webp_compress  # noqa: F401
+from . import method0409  # noqa: F401  (the 0409 notebook's own UNet: method0409.JPEGDiffusionModel)
 from .losses import color_loss, color_preservation_loss, frequency_aware_loss  # noqa: F401
 from .models import AVIFDiffusionModel, JPEGDiffusionModel, WebPDiffusionModel  # noqa: F401
 from .samplers import (DDRMAVIFSampler, DDRMJPEGSampler, DDRMWebPSampler, GaussianMixtureSampler,  # noqa: F401

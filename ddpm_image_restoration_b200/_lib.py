@@ -50,6 +50,7 @@ _SIGNATURES = {
     "ddpmir_conv3x3": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
     "ddpmir_gemm": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
     "ddpmir_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "ddpmir_channel_scale_add": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P, c_int, _P]),
     "ddpmir_jpeg_dct_project": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P]),
     "ddpmir_attention_prescaled_workspace": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "ddpmir_attention_prescaled": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),

@@ -320,6 +320,31 @@ extern "C" int ddpmir_avgpool_pyramid(const void* x, int dtype, int B, int H, in
     return DDPMIR_OK;
 }
 
+// out = x + y * s[b, c]  (FrequencyAwareBlock of the 0409 UNet, 0409_method.ipynb#c0:L256-263: x + x_freq * attn with a
+// per-image, per-channel squeeze-excite gate); x and y fp32 NHWC, optional second copy of the result in the operand dtype
+template <typename T2>
+__global__ void __launch_bounds__(256)
+channel_scale_add_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ s, float* __restrict__ out,
+                         T2* __restrict__ out2, long long HW, int C, long long total) {
+    const int cv = C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % cv);
+        const long long b = i / cv / HW;
+        const float* sp = s + b * C + v * 8;
+        Vec8<float> xv, yv;
+        xv.load(x + i * 8); yv.load(y + i * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xv.v[k] = fmaf(yv.v[k], sp[k], xv.v[k]);
+        xv.store(out + i * 8);
+        if (out2) {
+            Vec8<T2> ov;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ov.v[k] = xv.v[k];
+            ov.store(out2 + i * 8);
+        }
+    }
+}
+
 extern "C" int ddpmir_avif_combine(const void* h, int h_dtype, const void* xt, const float* gates, const void* color,
                                    const void* edge, int dtype, int B, int H, int W, int C, void* out,
                                    ddpmir_stream_t stream) {
@@ -330,6 +355,19 @@ extern "C" int ddpmir_avif_combine(const void* h, int h_dtype, const void* xt, c
     if (dtype == DDPMIR_F32) { DDPMIR_CHECK_ARG(h_dtype == DDPMIR_F32, "avif_combine: fp32 mode needs fp32 h"); GO(float, float); }
     else { if (h_dtype == DDPMIR_F32) GO(float, bf16); else GO(bf16, bf16); }
 #undef GO
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+extern "C" int ddpmir_channel_scale_add(const float* x, const float* y, const float* s, int B, long long HW, int C, float* out,
+                                        void* out2, int out2_dtype, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(x && y && s && out && B > 0 && HW > 0 && C > 0 && C % 8 == 0, "channel_scale_add: bad arguments");
+    const long long total = (long long)B * HW * (C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out2 && out2_dtype == DDPMIR_BF16)
+        channel_scale_add_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(x, y, s, out, (bf16*)out2, HW, C, total);
+    else
+        channel_scale_add_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(x, y, s, out, (float*)out2, HW, C, total);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

@@ -98,6 +98,19 @@ def ddrm_update(x_theta, codec, y, t, sigma_scale, eta=0.85, eta_b=1.0, z=None, 
     return out
 
 
+def channel_scale_add(x, y, s, out2_dtype=None):
+    """x + y * s[b, c] on fp32 NHWC tensors; optionally also returns the result in out2_dtype (GEMM operand copy)."""
+    _f32(x, "x"); _f32(y, "y"); _f32(s, "s")
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    out2 = torch.empty(x.shape, dtype=out2_dtype, device=x.device) if out2_dtype not in (None, torch.float32) else None
+    rc = _lib.lib().ddpmir_channel_scale_add(_p(x), _p(y), _p(s), B, H * W, C, _p(out), _p(out2),
+                                             _code(out2.dtype) if out2 is not None else F32, _stream())
+    _lib.check(rc, "channel_scale_add")
+    LAUNCHES[0] += 1
+    return out if out2_dtype is None else (out, out2 if out2 is not None else out)
+
+
 def jpeg_dct_project(x, quality, in_scale=1.0, in_offset=0.0):
     """DCTProcessor.jpeg_compress (dct.ipynb#c2:L100-139) on fp32 NCHW images; (in_scale, in_offset) maps x to 0..255."""
     _f32(x, "x")

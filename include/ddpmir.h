@@ -232,6 +232,12 @@ size_t ddpmir_attention_prescaled_workspace(int B, int L, int heads);
 int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
                                ddpmir_stream_t stream);
 
+/* out = x + y * s[b, c] on fp32 NHWC tensors ([B, HW, C]); FrequencyAwareBlock.forward of the 0409 UNet
+ * (experiments/code/0409_method.ipynb#c0:L256-263: x + x_freq * attn, attn a per-image per-channel gate).  out2 (optional)
+ * receives a copy in out2_dtype for the GEMMs that read the result.  C % 8 == 0. */
+int ddpmir_channel_scale_add(const float* x, const float* y, const float* s, int B, long long HW, int C, float* out,
+                             void* out2, int out2_dtype, ddpmir_stream_t stream);
+
 /* DCT-domain JPEG projection: DCTProcessor.jpeg_compress, experiments/code/dct.ipynb#c2:L100-139, the
  * reference's pure-torch JPEG simulator: per channel and 8x8 block  c = DCT(x255 - 128);  c = round(c / Q) * Q  (luma
  * table for channel 0, chroma table otherwise, scaled by `quality` as at L105-112);  x255' = IDCT(c) + 128.  No colour

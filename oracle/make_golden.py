@@ -8,6 +8,7 @@ Fixtures (all small):
   ddrm_{webp,jpeg,avif}_32.npz   reference DDRM sampler, 6 steps, noise injected = oracle.restated.philox_normal
   gmm_jpeg_32.npz                reference GaussianMixtureSampler (0409), 8 steps, with SVD guide + phase consistency
   ops.npz                        codec round trips, phase_consistency, svd_structure_preservation, colour losses
+  unet_m0409_{32,64}.npz, gmm_m0409_32.npz   the 0409 notebook's own UNet and its GMM sampler on that model
   dct_jpeg.npz                   DCTProcessor.jpeg_compress (dct.ipynb#c2) at q 10/50/90 on two 16x24 images
   traj256_webp.npz               (--trajectory256) BASELINE config 1: one 256x256 WebP q=10 image, 80 steps, computed
                                  with the restated oracle (the verbatim reference cannot allocate 68.7 GB at 256x256)
@@ -150,6 +151,29 @@ def op_goldens():
     save("ops.npz", **d)
 
 
+def m0409_goldens():
+    """unet_m0409_{32,64}.npz + gmm_m0409_32.npz: the 0409 notebook's own UNet (HFCM / FrequencyAwareBlock) and its
+    GaussianMixtureSampler running on that native model."""
+    nsm = rl.load_0409_model()
+    nsm["device"] = torch.device("cpu")
+    m = nsm["JPEGDiffusionModel"]().eval()
+    m.load_state_dict(W.make_state_dict("m0409", 0))
+    for hw, b in ((32, 2), (64, 1)):
+        g = torch.Generator().manual_seed(300 + hw)
+        x = torch.randn(b, 3, hw, hw, generator=g) * 0.5
+        t = torch.tensor([0.37, 0.8][:b])
+        lvl = torch.tensor([0.2, 0.9][:b])
+        with torch.no_grad():
+            save(f"unet_m0409_{hw}.npz", x=x, t=t, level=lvl, out=m(x, t, lvl), out_nolevel=m(x, t))
+    ns9 = rl.load_0409()
+    clean = W.synthetic_images(2, 32, 32)
+    y = R.codec_roundtrip(clean, 10, "jpeg")
+    steps = 8
+    with _InjectNoise(range(steps - 1, 0, -1)):
+        out = ns9["GaussianMixtureSampler"](m, num_timesteps=100).sample(y.clone(), steps=steps)
+    save("gmm_m0409_32.npz", clean=clean, y=y, steps=steps, out=out, psnr_out=R.psnr(out, clean))
+
+
 def dct_goldens():
     """dct_jpeg.npz: DCTProcessor.jpeg_compress (dct.ipynb#c2) on 0..255 images, run with the reference's own scalar loops."""
     P = rl.load_dct_processor()["DCTProcessor"](torch.device("cpu"))
@@ -188,6 +212,6 @@ if __name__ == "__main__":
     if args.trajectory256:
         trajectory256(args.images)
     else:
-        for fn in (op_goldens, unet_goldens, sampler_goldens, dct_goldens):
+        for fn in (op_goldens, unet_goldens, sampler_goldens, dct_goldens, m0409_goldens):
             if not args.only or args.only in fn.__name__:
                 fn()

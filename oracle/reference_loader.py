@@ -132,3 +132,12 @@ def load_dct_processor():
                "torch = _TorchScalarCos()\n")
     ns = _exec(_slice(c2, [(43, 139)]), "ref_dct", prelude=prelude)
     return ns
+
+
+def load_0409_model():
+    """experiments/code/0409_method.ipynb cell 0 lines 1-19 (imports, device) + 84-318 + 371-428: TimeEmbedding, DCTLayer, HFCM,
+    FrequencyAwareBlock, ResAttnBlock and the notebook's JPEGDiffusionModel (the SVD/GMM solver's native UNet)."""
+    _install_stubs()
+    c0 = _nb_cell("experiments/code/0409_method.ipynb", 0)
+    ns = _exec(_slice(c0, [(1, 19), (84, 318), (371, 428)]), "ref_0409_model")
+    return ns

@@ -243,6 +243,70 @@ def unet_forward(sd: SD, x: torch.Tensor, t: torch.Tensor, level: Optional[torch
 
 
 # ----------------------------------------------------------------------------------------------------------
+# 0409 UNet variant: experiments/code/0409_method.ipynb cell 0, the model the SVD/GMM solver was
+# written for.  Same 13-block skeleton; blocks flagged below carry FrequencyAwareBlock + HFCM, the others none.
+# ----------------------------------------------------------------------------------------------------------
+FREQ_BLOCKS_0409 = ("down2", "down3", "bottleneck.0", "bottleneck.2", "up2", "up3")     # use_freq_guide=True, L378-397
+
+
+def freq_aware_block_0409(sd: SD, p: str, x: torch.Tensor, level: torch.Tensor) -> torch.Tensor:
+    """FrequencyAwareBlock.forward 0409_method.ipynb#c0:L234-263: x + conv3x3(DCT8(x)) * (SE-gate * (1 - level) + 0.5)."""
+    xf = F.conv2d(block_transform(x, dct_matrix(8)), sd[p + ".freq_conv.weight"], sd[p + ".freq_conv.bias"], padding=1)
+    a = xf.mean(dim=(2, 3), keepdim=True)
+    a = F.relu(F.conv2d(a, sd[p + ".freq_attn.1.weight"], sd[p + ".freq_attn.1.bias"]))
+    a = torch.sigmoid(F.conv2d(a, sd[p + ".freq_attn.3.weight"], sd[p + ".freq_attn.3.bias"]))
+    a = a * (1.0 - level.view(-1, 1, 1, 1)) + 0.5
+    return x + xf * a
+
+
+def hfcm_0409(sd: SD, p: str, x: torch.Tensor, level: torch.Tensor) -> torch.Tensor:
+    """HFCM.forward 0409_method.ipynb#c0:L197-218: conv1x1(x + sigmoid(conv3(relu(conv3(x)))) * DCT8(x) * (1 - level))."""
+    mask = _gate(sd, p + ".high_freq_attn", x, F.relu)
+    enhanced = x + mask * block_transform(x, dct_matrix(8)) * (1.0 - level.view(-1, 1, 1, 1))
+    return F.conv2d(enhanced, sd[p + ".conv_out.weight"], sd[p + ".conv_out.bias"])
+
+
+def res_attn_block_0409(sd: SD, p: str, x: torch.Tensor, t_emb: torch.Tensor, level) -> torch.Tensor:
+    """ResAttnBlock.forward 0409_method.ipynb#c0:L296-318 (eval mode).  Unlike the shipped families the attention output
+    REPLACES h (no residual around it), the activation is SiLU and there is no trailing 3x3 conv."""
+    in_c, out_c = x.shape[1], sd[p + ".conv1.weight"].shape[0]
+    h = F.group_norm(x, gn_groups(in_c), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps=1e-5)
+    h = F.conv2d(h, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = h + F.linear(t_emb, sd[p + ".time_proj.weight"], sd[p + ".time_proj.bias"])[..., None, None]
+    h = F.group_norm(h, gn_groups(out_c), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], eps=1e-5)
+    h = F.conv2d(F.silu(h), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    h = self_attention(sd, p + ".attn", h, 4)
+    if level is not None and p in FREQ_BLOCKS_0409:
+        h = freq_aware_block_0409(sd, p + ".freq_guide", h, level)
+        h = hfcm_0409(sd, p + ".hfcm", h, level)
+    if p + ".shortcut.weight" in sd:
+        x = F.conv2d(x, sd[p + ".shortcut.weight"], sd[p + ".shortcut.bias"])
+    return x + h
+
+
+def unet0409_forward(sd: SD, x: torch.Tensor, t: torch.Tensor, level: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """JPEGDiffusionModel.forward of the 0409 notebook (0409_method.ipynb#c0:L402-428): 1x1 output conv, no tanh."""
+    with torch.no_grad():
+        t_emb = time_embedding(sd, t)
+        if level is None:
+            level = t.clone()
+        blk = lambda p, z: res_attn_block_0409(sd, p, z, t_emb, level)
+        pool = lambda z: F.max_pool2d(z, 2)
+        d1 = blk("down1", x)
+        d2 = blk("down2", pool(d1))
+        d3 = blk("down3", pool(d2))
+        d4 = blk("down4", pool(d3))
+        d5 = blk("down5", pool(d4))
+        bn = blk("bottleneck.2", blk("bottleneck.1", blk("bottleneck.0", pool(d5))))
+        u1 = blk("up1", _up_cat(bn, d5))
+        u2 = blk("up2", _up_cat(u1, d4))
+        u3 = blk("up3", _up_cat(u2, d3))
+        u4 = blk("up4", _up_cat(u3, d2))
+        u5 = blk("up5", _up_cat(u4, d1))
+        return F.conv2d(u5, sd["out_conv.weight"], sd["out_conv.bias"])
+
+
+# ----------------------------------------------------------------------------------------------------------
 # host codec round trip (the data-consistency operator)
 # ----------------------------------------------------------------------------------------------------------
 def quantize_u8(x: torch.Tensor) -> torch.Tensor:

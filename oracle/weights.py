@@ -12,7 +12,7 @@ from typing import Dict
 
 import torch
 
-from .restated import BLOCKS, dct_matrix
+from .restated import BLOCKS, FREQ_BLOCKS_0409, dct_matrix
 
 
 def _gen(seed: int, key: str) -> torch.Generator:
@@ -22,8 +22,37 @@ def _gen(seed: int, key: str) -> torch.Generator:
     return g
 
 
+def shapes_0409() -> Dict[str, tuple]:
+    """Checkpoint layout of the 0409 notebook's JPEGDiffusionModel (0409_method.ipynb#c0:L371-400)."""
+    s: Dict[str, tuple] = {}
+    s["time_embed.proj.0.weight"] = (1024, 256); s["time_embed.proj.0.bias"] = (1024,)
+    s["time_embed.proj.2.weight"] = (256, 1024); s["time_embed.proj.2.bias"] = (256,)
+    for p, ci, co in BLOCKS:
+        s[f"{p}.norm1.weight"] = (ci,); s[f"{p}.norm1.bias"] = (ci,)
+        s[f"{p}.conv1.weight"] = (co, ci, 3, 3); s[f"{p}.conv1.bias"] = (co,)
+        s[f"{p}.time_proj.weight"] = (co, 256); s[f"{p}.time_proj.bias"] = (co,)
+        s[f"{p}.norm2.weight"] = (co,); s[f"{p}.norm2.bias"] = (co,)
+        s[f"{p}.conv2.weight"] = (co, co, 3, 3); s[f"{p}.conv2.bias"] = (co,)
+        s[f"{p}.attn.in_proj_weight"] = (3 * co, co); s[f"{p}.attn.in_proj_bias"] = (3 * co,)
+        s[f"{p}.attn.out_proj.weight"] = (co, co); s[f"{p}.attn.out_proj.bias"] = (co,)
+        if ci != co:
+            s[f"{p}.shortcut.weight"] = (co, ci, 1, 1); s[f"{p}.shortcut.bias"] = (co,)
+        if p in FREQ_BLOCKS_0409:
+            f, h = f"{p}.freq_guide", f"{p}.hfcm"
+            s[f"{f}.freq_conv.weight"] = (co, co, 3, 3); s[f"{f}.freq_conv.bias"] = (co,)
+            s[f"{f}.freq_attn.1.weight"] = (co // 4, co, 1, 1); s[f"{f}.freq_attn.1.bias"] = (co // 4,)
+            s[f"{f}.freq_attn.3.weight"] = (co, co // 4, 1, 1); s[f"{f}.freq_attn.3.bias"] = (co,)
+            s[f"{h}.high_freq_attn.0.weight"] = (co, co, 3, 3); s[f"{h}.high_freq_attn.0.bias"] = (co,)
+            s[f"{h}.high_freq_attn.2.weight"] = (co, co, 3, 3); s[f"{h}.high_freq_attn.2.bias"] = (co,)
+            s[f"{h}.conv_out.weight"] = (co, co, 1, 1); s[f"{h}.conv_out.bias"] = (co,)
+    s["out_conv.weight"] = (3, 64, 1, 1); s["out_conv.bias"] = (3,)
+    return s
+
+
 def shapes(family: str) -> Dict[str, tuple]:
-    """Checkpoint layout of {WebP,JPEG,AVIF}DiffusionModel (356 / 356 / 634 entries)."""
+    """Checkpoint layout of {WebP,JPEG,AVIF}DiffusionModel (356 / 356 / 634 entries); "m0409" = the 0409 notebook's model."""
+    if family == "m0409":
+        return shapes_0409()
     s: Dict[str, tuple] = {}
     s["time_embed.proj.0.weight"] = (1024, 256); s["time_embed.proj.0.bias"] = (1024,)
     s["time_embed.proj.2.weight"] = (256, 1024); s["time_embed.proj.2.bias"] = (256,)

@@ -85,3 +85,28 @@ def test_unet_512_bf16_vs_check_mode():
     ref = m.set_precision("fp32")(x.cuda(), t.cuda()).cpu()
     out = m.set_precision("bf16")(x.cuda(), t.cuda()).cpu()
     assert torch.isfinite(out).all() and rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("hw", [32, 64])
+def test_m0409_unet_vs_reference_golden(golden, hw):
+    """The 0409 notebook's own UNet (HFCM / FrequencyAwareBlock, 1x1 output conv) against the reference's outputs."""
+    from ddpm_image_restoration_b200 import method0409
+    d = golden(f"unet_m0409_{hw}.npz")
+    m = method0409.JPEGDiffusionModel()
+    m.load_state_dict(W.make_state_dict("m0409", 0))
+    m = m.cuda().eval()
+    x, t, lvl = (torch.from_numpy(d[k]).cuda() for k in ("x", "t", "level"))
+    for precision, tol in (("fp32", 1e-5), ("bf16", 1e-2)):
+        m.set_precision(precision)
+        assert rel(m(x, t, lvl).cpu(), torch.from_numpy(d["out"])) < tol, precision
+        assert rel(m(x, t).cpu(), torch.from_numpy(d["out_nolevel"])) < tol, precision
+
+
+def test_channel_scale_add():
+    from ddpm_image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x, y, s = torch.randn(3, 5, 7, 16, generator=g), torch.randn(3, 5, 7, 16, generator=g), torch.randn(3, 16, generator=g)
+    want = x + y * s[:, None, None, :]
+    out, out2 = ops.channel_scale_add(x.cuda(), y.cuda(), s.cuda(), out2_dtype=torch.bfloat16)
+    assert torch.equal(out.cpu(), torch.addcmul(x, y, s[:, None, None, :])) or rel(out.cpu(), want) < 1e-6
+    assert rel(out2.float().cpu(), want) < 4e-3

@@ -22,6 +22,18 @@ def test_checkpoint_layout(fam, cls, n):
     assert sum(p.numel() for p in m.parameters()) == {"webp": 114398409, "jpeg": 114398409, "avif": 158284137}[fam]
 
 
+def test_checkpoint_layout_m0409():
+    """0409 notebook's JPEGDiffusionModel: 282 entries, 119 873 161 parameters."""
+    from ddpm_image_restoration_b200 import method0409
+    m = method0409.JPEGDiffusionModel()
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == W.shapes("m0409") and len(sd) == 282
+    m.load_state_dict(W.make_state_dict("m0409", 0))
+    assert sum(p.numel() for p in m.parameters()) == 119873161
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.zeros(1, 3, 32, 32), torch.zeros(1))     # CPU tensors: no fallback
+
+
 @pytest.mark.parametrize("codec,q", [("webp", 10), ("webp", 0), ("avif", 20), ("jpeg", 10), ("jpeg", 50), ("jpeg", 150)])
 def test_codec_pool_matches_oracle(codec, q):
     from ddpm_image_restoration_b200 import codec as C

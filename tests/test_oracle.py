@@ -131,3 +131,16 @@ def test_dct_jpeg_projection_vs_reference_fixture(golden):
     # projection: applying it twice changes nothing beyond rounding
     once = R.dct_jpeg_project(x, 50)
     assert (R.dct_jpeg_project(once, 50) - once).abs().max() < 1e-3
+
+
+def test_m0409_unet_and_gmm_oracle_vs_reference_fixture(golden):
+    """The 0409 notebook's own UNet (HFCM, FrequencyAwareBlock; 0409_method.ipynb#c0:L184-428) and its GMM sampler on it."""
+    sd = W.make_state_dict("m0409", 0)
+    d = golden("unet_m0409_32.npz")
+    x, t, lvl = (torch.from_numpy(d[k]) for k in ("x", "t", "level"))
+    assert rel(R.unet0409_forward(sd, x, t, lvl), torch.from_numpy(d["out"])) < 2e-5
+    assert rel(R.unet0409_forward(sd, x, t), torch.from_numpy(d["out_nolevel"])) < 2e-5
+    d = golden("gmm_m0409_32.npz")
+    out = R.gmm_sample(lambda x, t, l: R.unet0409_forward(sd, x, t, l), torch.from_numpy(d["y"]), int(d["steps"]),
+                       noise_fn=philox_noise, coin_fn=coin)
+    assert rel(out, torch.from_numpy(d["out"])) < 2e-5

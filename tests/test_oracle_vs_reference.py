@@ -64,3 +64,19 @@ def test_dct_processor_against_reference():
     x = torch.rand(1, 3, 8, 16, generator=g) * 255
     for q in (5, 50, 95):
         assert (P.jpeg_compress(x, quality=q) - R.dct_jpeg_project(x, q)).abs().max() < 1e-3
+
+
+def test_m0409_model_against_reference():
+    """experiments/code/0409_method.ipynb cell 0: the notebook's own UNet against the functional restatement."""
+    ns = rl.load_0409_model()
+    ns["device"] = torch.device("cpu")
+    m = ns["JPEGDiffusionModel"]().eval()
+    sd = W.make_state_dict("m0409", 0)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == W.shapes("m0409")
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    x, t = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1, torch.tensor([0.7, 0.25])
+    with torch.no_grad():
+        assert rel(R.unet0409_forward(sd, x, t), m(x, t)) < 2e-6
+        lvl = torch.tensor([0.3, 0.9])
+        assert rel(R.unet0409_forward(sd, x, t, lvl), m(x, t, lvl)) < 2e-6
