@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--projection", default="codec", choices=["codec", "dct"],
+                    help="data-consistency step: the reference's host codec (default) or the opt-in device-only DCT-domain "
+                         "projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
@@ -281,7 +284,7 @@ def main():
     def run(n_steps, warm, host_io):
         """Times n_steps timesteps (after `warm` untimed ones) -> (device ms, stats).  host_io: the trajectory starts
         from the pinned host batch and ends with the restored batch copied back to the host (the e2e arm)."""
-        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches)
+        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches, projection=args.projection)
         y_dev = y_host.to(dev, non_blocking=True)
         st = sampler.begin(y_dev, q, steps=traj)
         i = traj - 1
@@ -315,7 +318,7 @@ def main():
                               finite=bool(torch.isfinite(st["x_t"]).all()))
 
     if args.profile_ops and rank == 0:
-        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches)
+        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches, projection=args.projection)
         st = sampler.begin(y_host.to(dev), q, steps=traj)
         for i in (traj - 1, traj - 2):
             sampler.step(st, i)
@@ -393,6 +396,7 @@ def main():
             "config": {"workload": f"{fam}_inference.py DDRM sampling: batch {B}/GPU {fam.upper()}(q={q}) {H}x{Wd}, "
                                    f"{traj} timesteps/trajectory, step = one timestep over the batch",
                        "batch_per_gpu": B, "timesteps_per_trajectory": traj, "micro_batches": args.micro_batches,
+                       "projection": args.projection,
                        "codec_threads_per_rank": codec.pool_threads(), "host_cores": host_cores,
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": stats_e2e["h2d"] / K,
