@@ -42,9 +42,9 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--projection", default="codec", choices=["codec", "dct"],
-                    help="data-consistency step: the reference's host codec (default) or the opt-in device-only DCT-domain "
-                         "projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
+    ap.add_argument("--projection", default="codec", choices=["codec", "dct", "device"],
+                    help="data-consistency step: the reference's host codec (default), the bit-exact device JPEG round trip "
+                         "(--family jpeg only) or the opt-in DCT-domain projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],

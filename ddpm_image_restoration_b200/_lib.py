@@ -51,6 +51,8 @@ _SIGNATURES = {
     "ddpmir_gemm": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, ctypes.POINTER(Epilogue), _P, c_int, _P]),
     "ddpmir_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "ddpmir_channel_scale_add": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P, c_int, _P]),
+    "ddpmir_jpeg_roundtrip_workspace": (ctypes.c_size_t, [c_int, c_int, c_int]),
+    "ddpmir_jpeg_roundtrip_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_jpeg_dct_project": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P]),
     "ddpmir_attention_prescaled_workspace": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "ddpmir_attention_prescaled": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),

@@ -111,6 +111,21 @@ def channel_scale_add(x, y, s, out2_dtype=None):
     return out if out2_dtype is None else (out, out2 if out2 is not None else out)
 
 
+def jpeg_roundtrip_u8(rgb_u8, quality, out=None):
+    """Bit-exact device version of the Pillow JPEG round trip of jpeg_compress (svd.ipynb#c1:L20-44): uint8 [B,H,W,3] in
+    and out, 4:4:4 above quality 30 and 4:2:0 otherwise.  Raises DdpmirError for sizes that need MCU edge padding."""
+    if rgb_u8.dtype != torch.uint8 or rgb_u8.dim() != 4 or rgb_u8.shape[-1] != 3:
+        raise _lib.DdpmirError("jpeg_roundtrip_u8 needs a uint8 [B,H,W,3] tensor")
+    B, H, W, _ = rgb_u8.shape
+    q = max(1, min(100, int(quality)))
+    out = torch.empty_like(rgb_u8) if out is None else out
+    ws = torch.empty((_lib.lib().ddpmir_jpeg_roundtrip_workspace(B, H, W),), dtype=torch.uint8, device=rgb_u8.device)
+    rc = _lib.lib().ddpmir_jpeg_roundtrip_u8(_p(rgb_u8), _p(out), B, H, W, q, int(q <= 30), _p(ws), _stream())
+    _lib.check(rc, "jpeg_roundtrip_u8")
+    LAUNCHES[0] += 3
+    return out
+
+
 def jpeg_dct_project(x, quality, in_scale=1.0, in_offset=0.0):
     """DCTProcessor.jpeg_compress (dct.ipynb#c2:L100-139) on fp32 NCHW images; (in_scale, in_offset) maps x to 0..255."""
     _f32(x, "x")

@@ -31,11 +31,14 @@ class _DDRMSampler:
     family = None
 
     def __init__(self, model, seed=0, micro_batches=None, noise_fn=None, projection="codec"):
-        """projection: "codec" = the reference's host codec round trip (Pillow, bit-identical bytes); "dct" = opt-in GPU
-        data-consistency projection in the DCT domain (DCTProcessor.jpeg_compress, dct.ipynb#c2:L100-139):
-        no host hop, NOT libjpeg -- results differ from the codec path and are checked by PSNR, not bit-exactly."""
-        if projection not in ("codec", "dct"):
+        """projection: "codec" = the reference's host codec round trip (Pillow); "device" = JPEG family only: the same
+        round trip computed on the GPU with libjpeg-turbo's integer arithmetic (ddpmir_jpeg_roundtrip_u8) -- bit-identical
+        pixels, no host hop; "dct" = opt-in DCT-domain projection as the reference's DCTProcessor defines it
+        (dct.ipynb#c2:L100-139) -- NOT libjpeg, results differ from the codec path and are checked by PSNR."""
+        if projection not in ("codec", "dct", "device"):
             raise ValueError(projection)
+        if projection == "device" and self.family != "jpeg":
+            raise ValueError("projection='device' exists for the JPEG codec only (WebP and AVIF stay on the host)")
         self.model = model
         self.seed = seed
         self.micro_batches = micro_batches
@@ -95,7 +98,7 @@ class _DDRMSampler:
         import time
         cfg, y, chunks = st["cfg"], st["y"], st["chunks"]
         B, C, H, W = st["x_t"].shape
-        if self.projection == "dct":
+        if self.projection != "codec":
             return self._step_dct(st, i)
         with torch.no_grad():
             for k in range(len(chunks)):
@@ -138,7 +141,7 @@ class _DDRMSampler:
         return st["x_t"]
 
     def _step_dct(self, st, i):
-        """The same timestep with the DCT-domain projection instead of the host codec: everything stays on the device."""
+        """The same timestep with a device-side data-consistency operator instead of the host codec."""
         cfg, y = st["cfg"], st["y"]
         B, C, H, W = st["x_t"].shape
         x_cur, x_new = st["x_t"], st["x_alt"]
@@ -146,7 +149,10 @@ class _DDRMSampler:
             for s, e in st["chunks"]:
                 t = torch.full((e - s,), float(i) / st["steps"], dtype=torch.float32, device=x_cur.device)
                 x_theta = self.model(x_cur[s:e], t, t)
-                proj = ops.jpeg_dct_project(x_theta, st["quality"], 127.5, 127.5)
+                if self.projection == "device":      # raw decoder bytes, exactly what the host codec would hand back
+                    proj = ops.jpeg_roundtrip_u8(ops.quantize_u8_hwc(x_theta), st["quality"])
+                else:
+                    proj = ops.jpeg_dct_project(x_theta, st["quality"], 127.5, 127.5)
                 z = None
                 if self.noise_fn is not None and i > 0:
                     z = self.noise_fn(i, x_cur)[s:e].contiguous()

@@ -204,3 +204,48 @@ def test_gmm_sampler_on_its_native_0409_model(golden):
         out = s.sample(y.cuda(), steps=int(d["steps"])).cpu()
         assert rel(out, torch.from_numpy(d["out"])) < tol, precision
         assert abs(R.psnr(out, clean) - float(d["psnr_out"])) < 0.05
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (64, 96), (256, 256)])
+def test_device_jpeg_roundtrip_is_bit_exact(hw):
+    """ddpmir_jpeg_roundtrip_u8 against Pillow itself (the codec the reference calls) and the integer oracle: every byte."""
+    from ddpm_image_restoration_b200 import codec as C, ops
+    from oracle import jpeg_exact as J
+    H, W = hw
+    rng = np.random.default_rng(H + W)
+    yy, xx = np.mgrid[0:H, 0:W]
+    smooth = (127 + 110 * np.sin(xx / 9.0) * np.cos(yy / 13.0))[None, :, :, None] + rng.normal(0, 10, (1, H, W, 3))
+    noise = rng.integers(0, 256, (1, H, W, 3))
+    edges = np.zeros((1, H, W, 3)); edges[:, :, W // 2:] = 255; edges[:, H // 2:, :, 1] = 200
+    imgs = np.concatenate([smooth, noise, edges]).clip(0, 255).astype(np.uint8)
+    for q in (1, 5, 10, 30, 31, 50, 90, 100) if H < 256 else (10, 50):
+        want = C.roundtrip_u8("jpeg", q, imgs)
+        got = ops.jpeg_roundtrip_u8(torch.from_numpy(imgs).cuda(), q).cpu().numpy()
+        assert np.array_equal(got, want), q
+        assert np.array_equal(J.roundtrip_rgb(imgs[0], q, q <= 30), want[0])
+    with pytest.raises(Exception):
+        ops.jpeg_roundtrip_u8(torch.zeros(1, 24, 24, 3, dtype=torch.uint8, device="cuda"), 10)     # 4:2:0 needs multiples of 16
+
+
+def test_ddrm_jpeg_sampler_device_codec_equals_host_codec():
+    """projection="device" against the host-codec sampler.  The codec bytes are identical (test above) and the rest of the
+    step runs the same kernels, so one step agrees except where run-to-run noise of the GroupNorm atomics (1e-7) pushes a
+    value across a uint8 truncation boundary; over several steps of a random-init network such a flip is amplified, so longer
+    trajectories are compared on restoration quality, like the other sampler tests."""
+    import ddpm_image_restoration_b200 as P
+    clean = W.synthetic_images(2, 64, 64, seed=21)
+    for quality in (10, 50):
+        y = R.codec_roundtrip(clean, quality, "jpeg")
+        for precision in ("fp32", "bf16"):
+            m = load_model("jpeg").set_precision(precision)
+            host = P.DDRMJPEGSampler(m, seed=NOISE_SEED).sample(y.cuda(), quality, steps=1).cpu()
+            dev = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="device").sample(y.cuda(), quality, steps=1).cpu()
+            d = (host - dev).abs()
+            if precision == "fp32":      # in bf16 a 1e-7 difference flips bf16 roundings upstream and then uint8 truncations
+                assert torch.median(d) < 1e-5 and (d > 0.05).float().mean() < 0.02, quality
+            assert abs(R.psnr(dev, clean) - R.psnr(host, clean)) < 0.3, (quality, precision)
+            host = P.DDRMJPEGSampler(m, seed=NOISE_SEED).sample(y.cuda(), quality, steps=5).cpu()
+            dev = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="device").sample(y.cuda(), quality, steps=5).cpu()
+            assert abs(R.psnr(dev, clean) - R.psnr(host, clean)) < 0.3, (quality, precision)
+    with pytest.raises(ValueError):
+        P.DDRMWebPSampler(load_model("webp"), projection="device")

@@ -144,3 +144,22 @@ def test_m0409_unet_and_gmm_oracle_vs_reference_fixture(golden):
     out = R.gmm_sample(lambda x, t, l: R.unet0409_forward(sd, x, t, l), torch.from_numpy(d["y"]), int(d["steps"]),
                        noise_fn=philox_noise, coin_fn=coin)
     assert rel(out, torch.from_numpy(d["out"])) < 2e-5
+
+
+def test_jpeg_exact_restatement_vs_pillow():
+    """oracle/jpeg_exact.py (libjpeg-turbo's integer pipeline restated) against Pillow's own JPEG round trip: bit-exact."""
+    from oracle import jpeg_exact as J
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        H, W = 16 * int(rng.integers(1, 4)), 16 * int(rng.integers(1, 5))
+        if trial % 3 == 0:
+            img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        elif trial % 3 == 1:
+            yy, xx = np.mgrid[0:H, 0:W]
+            base = 127 + 110 * np.sin(xx / rng.uniform(3, 20)) * np.cos(yy / rng.uniform(3, 20))
+            img = (np.stack([base, base[::-1], 255 - base], -1) + rng.normal(0, 15, (H, W, 3))).clip(0, 255).astype(np.uint8)
+        else:
+            img = np.zeros((H, W, 3), np.uint8); img[:, W // 2:] = 255; img[H // 2:, :, 1] = 77
+        for q in (1, 10, 30, 31, 50, 75, 95, 100):
+            sub = 0 if q > 30 else 2          # jpeg_compress: 4:4:4 above quality 30, 4:2:0 otherwise
+            assert np.array_equal(J.pil_roundtrip(img, q, "RGB", sub), J.roundtrip_rgb(img, q, sub == 2)), (trial, q)
