@@ -42,8 +42,9 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--projection", default="codec", choices=["codec", "dct", "device"],
-                    help="data-consistency step: the reference's host codec (default), the bit-exact device JPEG round trip "
+    ap.add_argument("--projection", default="auto", choices=["auto", "codec", "dct", "device"],
+                    help="data-consistency step: auto (default: device JPEG codec for --family jpeg, host codec otherwise), the "
+                         "reference's host codec, the bit-exact device JPEG round trip "
                          "(--family jpeg only) or the opt-in DCT-domain projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")

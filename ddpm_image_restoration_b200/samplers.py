@@ -30,12 +30,13 @@ _DDRM = {
 class _DDRMSampler:
     family = None
 
-    def __init__(self, model, seed=0, micro_batches=None, noise_fn=None, projection="codec"):
-        """projection: "codec" = the reference's host codec round trip (Pillow); "device" = JPEG family only: the same
+    def __init__(self, model, seed=0, micro_batches=None, noise_fn=None, projection="auto"):
+        """projection: "auto" (default) = "device" where it exists (JPEG family, sizes without MCU edge padding), else
+        "codec"; "codec" = the reference's host codec round trip (Pillow); "device" = JPEG family only: the same
         round trip computed on the GPU with libjpeg-turbo's integer arithmetic (ddpmir_jpeg_roundtrip_u8) -- bit-identical
         pixels, no host hop; "dct" = opt-in DCT-domain projection as the reference's DCTProcessor defines it
         (dct.ipynb#c2:L100-139) -- NOT libjpeg, results differ from the codec path and are checked by PSNR."""
-        if projection not in ("codec", "dct", "device"):
+        if projection not in ("auto", "codec", "dct", "device"):
             raise ValueError(projection)
         if projection == "device" and self.family != "jpeg":
             raise ValueError("projection='device' exists for the JPEG codec only (WebP and AVIF stay on the host)")
@@ -65,7 +66,12 @@ class _DDRMSampler:
         B, C, H, W = x_t.shape
         chunks = self._chunks(B)
         use_phase = quality < cfg["q_thr"]
-        st = dict(cfg=cfg, x_t=x_t, x_alt=torch.empty_like(x_t), y=x_t.clone(), quality=quality, steps=steps, eta=eta, eta_b=eta_b,
+        projection = self.projection
+        if projection == "auto":
+            q = max(1, min(100, int(quality)))
+            mcu = 16 if q <= 30 else 8                      # jpeg_compress: 4:2:0 up to quality 30, 4:4:4 above
+            projection = "device" if (self.family == "jpeg" and H % mcu == 0 and W % mcu == 0) else "codec"
+        st = dict(projection=projection, cfg=cfg, x_t=x_t, x_alt=torch.empty_like(x_t), y=x_t.clone(), quality=quality, steps=steps, eta=eta, eta_b=eta_b,
                   chunks=chunks, use_phase=use_phase, h2d=0, d2h=0, codec_s=0.0, pending=[None] * len(chunks),
                   phasor=ops.phase_reference(x_t) if (use_phase and steps > cfg["period"]) else None)
         # staging: device uint8 buffers and pinned host buffers, one set per micro-batch
@@ -98,7 +104,7 @@ class _DDRMSampler:
         import time
         cfg, y, chunks = st["cfg"], st["y"], st["chunks"]
         B, C, H, W = st["x_t"].shape
-        if self.projection != "codec":
+        if st["projection"] != "codec":
             return self._step_dct(st, i)
         with torch.no_grad():
             for k in range(len(chunks)):
@@ -149,7 +155,7 @@ class _DDRMSampler:
             for s, e in st["chunks"]:
                 t = torch.full((e - s,), float(i) / st["steps"], dtype=torch.float32, device=x_cur.device)
                 x_theta = self.model(x_cur[s:e], t, t)
-                if self.projection == "device":      # raw decoder bytes, exactly what the host codec would hand back
+                if st["projection"] == "device":     # raw decoder bytes, exactly what the host codec would hand back
                     proj = ops.jpeg_roundtrip_u8(ops.quantize_u8_hwc(x_theta), st["quality"])
                 else:
                     proj = ops.jpeg_dct_project(x_theta, st["quality"], 127.5, 127.5)

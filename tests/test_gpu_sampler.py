@@ -238,13 +238,13 @@ def test_ddrm_jpeg_sampler_device_codec_equals_host_codec():
         y = R.codec_roundtrip(clean, quality, "jpeg")
         for precision in ("fp32", "bf16"):
             m = load_model("jpeg").set_precision(precision)
-            host = P.DDRMJPEGSampler(m, seed=NOISE_SEED).sample(y.cuda(), quality, steps=1).cpu()
+            host = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="codec").sample(y.cuda(), quality, steps=1).cpu()
             dev = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="device").sample(y.cuda(), quality, steps=1).cpu()
             d = (host - dev).abs()
             if precision == "fp32":      # in bf16 a 1e-7 difference flips bf16 roundings upstream and then uint8 truncations
                 assert torch.median(d) < 1e-5 and (d > 0.05).float().mean() < 0.02, quality
             assert abs(R.psnr(dev, clean) - R.psnr(host, clean)) < 0.3, (quality, precision)
-            host = P.DDRMJPEGSampler(m, seed=NOISE_SEED).sample(y.cuda(), quality, steps=5).cpu()
+            host = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="codec").sample(y.cuda(), quality, steps=5).cpu()
             dev = P.DDRMJPEGSampler(m, seed=NOISE_SEED, projection="device").sample(y.cuda(), quality, steps=5).cpu()
             assert abs(R.psnr(dev, clean) - R.psnr(host, clean)) < 0.3, (quality, precision)
     with pytest.raises(ValueError):
