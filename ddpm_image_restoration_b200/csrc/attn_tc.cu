@@ -25,7 +25,10 @@ namespace {
 
 constexpr int TQ = 128;                         // query rows per CTA
 constexpr int TK = 64;                          // keys per tile
-constexpr int NWG = 4;                          // softmax warpgroups
+constexpr int NWG = 2;                          // softmax warpgroups per CTA
+constexpr int CTAS_PER_SM = 2;                  // two CTAs share an SM (and its 512 TMEM columns): one CTA's prologue, pipeline
+                                                // fill and epilogue run under the other's main loop
+constexpr int TMEM_COLS = 512 / CTAS_PER_SM;
 constexpr int NBUF = 1;                         // S/P buffers per warpgroup: the next S tiles are ready before the current one is done
 constexpr int LAG = NWG * NBUF;                 // S/P buffers in flight
 constexpr int NSTAGE = 10;                      // K/V ring (a stage is released by the PV of its tile)
@@ -65,7 +68,7 @@ __device__ __forceinline__ float sumsq_bf16x2(uint32_t v) {
 
 // POLY of every 8 score pairs take the FMA-pipe exp2
 template <int HD, int POLY, int DEG>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out, const float* __restrict__ kmax, int* __restrict__ flags,
                int L, int C) {
     constexpr int KB = HD / 8;                  // 16-byte blocks per Q / K row that hold data (the MMA always reads 2: K = 16)
@@ -112,7 +115,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         }
     }
     fence_proxy_async();
-    if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -153,7 +156,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         const int bad = __syncthreads_or(!(bound <= BOUND_LIMIT));
         if (tid == 0) flags[((long long)b * gridDim.y + h) * gridDim.x + blockIdx.x] = bad;
         if (bad) {
-            if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+            if (warp == W_MMA) tmem_dealloc(tmem_base, TMEM_COLS);
             return;
         }
     }
@@ -293,7 +296,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 template <int HD, int POLY, int DEG>
@@ -301,7 +304,9 @@ int launch(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int 
     constexpr int NO = HD == 8 ? 16 : 32;
     // the kernel owns all 512 TMEM columns, so exactly one CTA may live on an SM: ask for more than half of the shared memory
     constexpr int need = NSTAGE * (2 + NO / 8) * BLK + 2 * QBLK + (2 * NSTAGE + 2 * LAG + 2 * NWG + 2) * 8 + 16 + 128;
-    constexpr int smem = need > 120 * 1024 ? need : 120 * 1024;
+    constexpr int floor_bytes = (227 * 1024) / (CTAS_PER_SM + 1) + 1024;     // no more than CTAS_PER_SM CTAs fit an SM
+    constexpr int smem = need > floor_bytes ? need : floor_bytes;
+    static_assert(LAG * TK + NWG * (TK / 2) + 32 <= TMEM_COLS, "TMEM budget");
     auto kern = attn_tc_kernel<HD, POLY, DEG>;
     static bool attr_set = false;
     if (!attr_set) {
