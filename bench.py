@@ -369,7 +369,7 @@ def main():
         roof = {"bound": "tensor", "kernel": f"attn_tc_kernel<hd={64 // heads}> (tcgen05/TMEM bounded-softmax self-attention, full resolution, L={H * Wd})",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 # dram__bytes_read+write of this launch from profiles/r1_attn_tc_ncu_metrics.csv (ncu --set full, same shape)
-                "traffic": 539.06e6 if (fam == "avif" and bsz == 16 and H * Wd == 65536) else None,
+                "traffic": 544.6e6 if (fam == "avif" and bsz == 16 and H * Wd == 65536) else None,
                 "algorithmic_bytes": bsz * H * Wd * 64 * 2 * 4,
                 "peak_source": pk["src"] + " (sustained bf16 GEMM)", "launch_ms": avg_ms,
                 "launches_timed": len(attn), "share_of_step": sum(m for m, _ in attn) / ms,
