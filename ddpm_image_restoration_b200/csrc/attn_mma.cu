@@ -717,15 +717,15 @@ extern "C" int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, 
         if (hd == 8) attn_kbound_kernel<8><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C);
         else attn_kbound_kernel<16><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C);
         DDPMIR_LAUNCH_CHECK();
-        // exp split (measured on B200, see profiles/): tcgen05 kernel -> 3 of 8 score pairs on the FMA pipe with the degree-2
-        // polynomial (11), mma.sync kernel -> 2 of 8 with degree 3 (2); the UNet's bf16 error is the same for all of them
-        const bool tc_ok = !(g_poly >= 0 && (g_poly & 16)) && L >= 1024 && L % 128 == 0;
-        const int sel = g_poly >= 0 ? g_poly : (tc_ok ? 11 : 2);
+        // exp split (measured on B200, see profiles/): tcgen05 kernel -> 3 of 8 score pairs on the FMA/ALU pipes as packed bf16
+        // pairs (19), mma.sync kernel -> 2 of 8 with the degree-3 fp32 polynomial (2); the UNet's bf16 error moves by < 4 %
+        const bool tc_ok = !(g_poly >= 0 && (g_poly & 64)) && L >= 1024 && L % 128 == 0;
+        const int sel = g_poly >= 0 ? g_poly : (tc_ok ? 19 : 2);
         const int poly = sel & 7;
         const bool rn = (sel & 8) != 0;   // +8: degree-2 polynomial
         int rc = DDPMIR_ERR_UNSUPPORTED;
-        // long sequences: tcgen05 / TMEM kernel (attn_tc.cu); +16 in the tuning hook keeps the mma.sync kernel
-        if (tc_ok) rc = ddpmir_attention_tc(qkv, out, kmax, flags, B, L, C, heads, sel & 15, st);
+        // long sequences: tcgen05 / TMEM kernel (attn_tc.cu); +64 in the tuning hook keeps the mma.sync kernel
+        if (tc_ok) rc = ddpmir_attention_tc(qkv, out, kmax, flags, B, L, C, heads, sel & 31, st);
         if (rc == DDPMIR_ERR_UNSUPPORTED) {
 #define GB(HD) (rn ? (poly == 0 ? launch_bounded<HD, 0, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \
                       poly == 1 ? launch_bounded<HD, 1, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \

@@ -61,6 +61,27 @@ __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
     asm("prmt.b32 %0, %1, %2, 0x7632;\n" : "=r"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
     return r;
 }
+// exp2 of a PAIR of scores on the FMA / ALU pipes, produced directly as packed bf16 (DEG == 1): no MUFU, no fp32 polynomial,
+// no separate pack.  |x| <= 60 (the kernel's logit bound).  t = x + (1.5 * 2^16 + 64) has ulp 2^-7, so the low 16 bits of
+// its encoding are N * 128 + F with N = floor(x) + 64 (7 bits) and F the 7-bit fraction of x (round to nearest): exactly the
+// exponent and mantissa fields of a bf16.  y = 1.F in [1, 2) is built by masking, 2^(y-1) comes from a degree-2 minimax
+// polynomial in two packed bf16 FMAs (max 0.57 %, rms 0.25 % relative error including the bf16 arithmetic, zero mean --
+// the same order as truncating an exact value to bf16, which the other pairs do), and the exponent N - 64 is added to both
+// halves with one integer add.
+__device__ __forceinline__ uint32_t ex2_pair_bf16(float x0, float x1) {
+    const float K = 98368.f;
+    const uint32_t t0 = __float_as_uint(x0 + K), t1 = __float_as_uint(x1 + K);
+    uint32_t w, q;
+    asm("prmt.b32 %0, %1, %2, 0x5410;\n" : "=r"(w) : "r"(t0), "r"(t1));
+    const uint32_t y = (w & 0x007F007Fu) | 0x3F803F80u;
+    const uint32_t e = w & 0x3F803F80u;
+    // 0.33713989 y^2 - 0.016585349 y + 0.68115741 as bf16 pairs
+    asm("{\n\t.reg .b32 u;\n\t"
+        "fma.rn.bf16x2 u, %1, %2, %3;\n\t"
+        "fma.rn.bf16x2 %0, u, %2, %4;\n\t}"
+        : "=r"(q) : "r"(0x3EAD3EADu), "r"(y), "r"(0xBC88BC88u), "r"(0x3F2E3F2Eu));
+    return q + e - 0x20002000u;
+}
 __device__ __forceinline__ float sumsq_bf16x2(uint32_t v) {
     const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
     return lo * lo + hi * hi;
@@ -231,8 +252,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
                 const bool poly = POLY == 1 ? i8 == 5 : POLY == 2 ? (i8 & 3) == 3 : POLY == 3 ? (i8 == 2 || i8 == 5 || i8 == 7)
                                 : POLY == 4 ? (i8 & 1) == 1 : POLY == 5 ? (i8 != 0 && i8 != 3 && i8 != 6) : false;
                 const float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
-                const float e0 = poly ? ex2_poly_bounded<DEG>(x0) : ex2f(x0);
-                const float e1 = poly ? ex2_poly_bounded<DEG>(x1) : ex2f(x1);
+                if (poly && DEG == 1) { pk[i] = ex2_pair_bf16(x0, x1); continue; }
+                const float e0 = poly ? ex2_poly_bounded<DEG == 1 ? 2 : DEG>(x0) : ex2f(x0);
+                const float e1 = poly ? ex2_poly_bounded<DEG == 1 ? 2 : DEG>(x1) : ex2f(x1);
                 pk[i] = pack_bf16_trunc(e0, e1);
             }
         };
@@ -323,7 +345,7 @@ int launch(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int 
 }  // namespace
 
 // qkv [B, L, 3C] bf16 with pre-scaled q; kmax [B*heads] from the key-norm pre-pass; flags [B*heads*L/128].
-// sel: bits 0-2 = score pairs of 8 on the FMA pipe, bit 3 = degree-2 polynomial.
+// sel: bits 0-2 = score pairs of 8 on the FMA pipe, bits 3-4 = how: 0 degree-3 fp32 polynomial, 1 degree 2, 2 packed bf16 pairs.
 int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, cudaStream_t st) {
     const int hd = C / heads;
     if ((hd != 8 && hd != 16) || L % TQ != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return DDPMIR_ERR_UNSUPPORTED;
@@ -340,20 +362,15 @@ int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flag
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { ddpmir_set_error("attention_tc: tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
     }
-    const int poly = sel & 7;
-    const bool d2 = (sel & 8) != 0;
-#define GT(HD) (d2 ? (poly == 0 ? launch<HD, 0, 2>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 1 ? launch<HD, 1, 2>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 2 ? launch<HD, 2, 2>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 3 ? launch<HD, 3, 2>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 4 ? launch<HD, 4, 2>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                                  launch<HD, 5, 2>(tm, out, kmax, flags, B, L, C, heads, st)) \
-                   : (poly == 0 ? launch<HD, 0, 3>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 1 ? launch<HD, 1, 3>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 2 ? launch<HD, 2, 3>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 3 ? launch<HD, 3, 3>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                      poly == 4 ? launch<HD, 4, 3>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                                  launch<HD, 5, 3>(tm, out, kmax, flags, B, L, C, heads, st)))
+    const int poly = sel & 7, mode = (sel >> 3) & 3;       // mode 0: degree-3 fp32 polynomial, 1: degree 2, 2: packed bf16 pairs
+#define GP(HD, DEG) (poly == 0 ? launch<HD, 0, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
+                     poly == 1 ? launch<HD, 1, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
+                     poly == 2 ? launch<HD, 2, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
+                     poly == 3 ? launch<HD, 3, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
+                     poly == 4 ? launch<HD, 4, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
+                                 launch<HD, 5, DEG>(tm, out, kmax, flags, B, L, C, heads, st))
+#define GT(HD) (mode == 2 ? GP(HD, 1) : mode == 1 ? GP(HD, 2) : GP(HD, 3))
     return hd == 8 ? GT(8) : GT(16);
 #undef GT
+#undef GP
 }

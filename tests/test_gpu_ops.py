@@ -348,12 +348,12 @@ def _prescaled(qkv, heads, gain=1.0):
     return pre.to(torch.bfloat16), ref
 
 
-@pytest.mark.parametrize("sel", [-1, 0, 1, 2, 3, 4, 5, 8, 11, 12, 18, 27])
+@pytest.mark.parametrize("sel", [-1, 0, 1, 2, 3, 4, 5, 8, 11, 12, 18, 19, 20, 21, 66, 75])
 @pytest.mark.parametrize("hd,heads,L", [(8, 8, 1024), (16, 4, 1024), (16, 8, 64), (8, 8, 4096), (8, 4, 192), (32, 4, 256), (64, 4, 128),
                                         (16, 4, 100), (256, 4, 64), (16, 8, 2048), (8, 4, 1152)])
 def test_attention_prescaled_bf16(ops, sel, hd, heads, L):
     """Bounded-softmax kernels (head_dim 8/16: tcgen05/TMEM kernel for L >= 1024 with L % 128 == 0, mma.sync kernel otherwise
-    or with +16 in the selector; every exp-pipe split) and the exact kernels behind the same entry point."""
+    or with +64 in the selector; every exp-pipe split: +8 degree-2 polynomial, +16 packed bf16 pairs) and the exact kernels behind the same entry point."""
     from ddpm_image_restoration_b200 import _lib
     if sel > 0 and hd > 16:
         pytest.skip("the split only exists in the bounded kernel")
@@ -401,7 +401,7 @@ def test_attention_full_resolution_kernels_agree(ops, hd, heads):
     qkv = torch.randn(1, L, 3 * C, generator=g(5)) * 1.2
     pre, ref = _prescaled(qkv, heads)
     out_tc = ops.attention_prescaled(pre.cuda(), heads).float()
-    _lib.lib().ddpmir_attention_set_expmode((18 + 1) << 8)    # +16: mma.sync bounded kernel
+    _lib.lib().ddpmir_attention_set_expmode((66 + 1) << 8)    # +64: mma.sync bounded kernel
     try:
         out_mma = ops.attention_prescaled(pre.cuda(), heads).float()
     finally:
