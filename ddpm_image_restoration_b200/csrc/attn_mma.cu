@@ -717,10 +717,10 @@ extern "C" int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, 
         if (hd == 8) attn_kbound_kernel<8><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C);
         else attn_kbound_kernel<16><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C);
         DDPMIR_LAUNCH_CHECK();
-        // exp split (measured on B200, see profiles/): tcgen05 kernel -> 3 of 8 score pairs on the FMA/ALU pipes as packed bf16
-        // pairs (19), mma.sync kernel -> 2 of 8 with the degree-3 fp32 polynomial (2); the UNet's bf16 error moves by < 4 %
+        // exp split (measured on B200, see profiles/): tcgen05 kernel -> every other score pair on the FMA/ALU pipes as packed
+        // bf16 (20), mma.sync kernel -> 2 of 8 with the degree-3 fp32 polynomial (2); the UNet's bf16 error moves by < 4 %
         const bool tc_ok = !(g_poly >= 0 && (g_poly & 64)) && L >= 1024 && L % 128 == 0;
-        const int sel = g_poly >= 0 ? g_poly : (tc_ok ? 19 : 2);
+        const int sel = g_poly >= 0 ? g_poly : (tc_ok ? 20 : 2);
         const int poly = sel & 7;
         const bool rn = (sel & 8) != 0;   // +8: degree-2 polynomial
         int rc = DDPMIR_ERR_UNSUPPORTED;

@@ -62,25 +62,30 @@ __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
     return r;
 }
 // exp2 of a PAIR of scores on the FMA / ALU pipes, produced directly as packed bf16 (DEG == 1): no MUFU, no fp32 polynomial,
-// no separate pack.  |x| <= 60 (the kernel's logit bound).  t = x + (1.5 * 2^16 + 64) has ulp 2^-7, so the low 16 bits of
-// its encoding are N * 128 + F with N = floor(x) + 64 (7 bits) and F the 7-bit fraction of x (round to nearest): exactly the
-// exponent and mantissa fields of a bf16.  y = 1.F in [1, 2) is built by masking, 2^(y-1) comes from a degree-2 minimax
-// polynomial in two packed bf16 FMAs (max 0.57 %, rms 0.25 % relative error including the bf16 arithmetic, zero mean --
-// the same order as truncating an exact value to bf16, which the other pairs do), and the exponent N - 64 is added to both
-// halves with one integer add.
+// no separate pack -- 7 instructions per pair, 2 of them on the (half-rate) ALU pipe.  |x| <= 60 (the kernel's logit bound).
+//   t = x + (2^16 + 64) lies in [2^16, 2^17), where an fp32 ulp is 2^-7: the low 16 bits of its encoding are N * 128 + F with
+//       N = floor(x) + 64 (7 bits) and F the 7-bit fraction of x (round to nearest) -- the exponent and mantissa fields of a
+//       bf16 -- and the high 16 bits are the constant 0x4780 = 143 * 128;
+//   w = t1 * 2^16 + t0 (one IMAD) therefore holds N0 * 128 + F0 in its low half and (N1 + 143) * 128 + F1 in its high half;
+//   y = 1.F in [1, 2) for both halves by one LOP3; q = 2^(y-1) by a degree-2 minimax polynomial in two packed bf16 FMAs
+//       (max 0.57 %, rms 0.25 % relative error including the bf16 arithmetic, zero mean: the order of truncating an exact
+//       value to bf16, which the MUFU pairs do), with the coefficients of the low half pre-scaled by 2^63 and those of the
+//       high half by 2^-80, so that
+//   r = q + w - y (one IADD3 on the whole word) lands on q * 2^(N - 64) in both halves: the fraction bits of w and y cancel,
+//       the exponent offsets (63 - 127 + 0 and -80 - 127 + 143) both come to -64.
 __device__ __forceinline__ uint32_t ex2_pair_bf16(float x0, float x1) {
-    const float K = 98368.f;
+    const float K = 65600.f;
     const uint32_t t0 = __float_as_uint(x0 + K), t1 = __float_as_uint(x1 + K);
     uint32_t w, q;
-    asm("prmt.b32 %0, %1, %2, 0x5410;\n" : "=r"(w) : "r"(t0), "r"(t1));
-    const uint32_t y = (w & 0x007F007Fu) | 0x3F803F80u;
-    const uint32_t e = w & 0x3F803F80u;
-    // 0.33713989 y^2 - 0.016585349 y + 0.68115741 as bf16 pairs
+    asm("mad.lo.u32 %0, %1, 65536, %2;\n" : "=r"(w) : "r"(t1), "r"(t0));
+    uint32_t y;            // (w & 0x007F007F) | 0x3F803F80 as ONE lop3: both masks must be register operands for that
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;\n" : "=r"(y) : "r"(w), "r"(0x007F007Fu), "r"(0x3F803F80u));
+    // 0.33789 y^2 - 0.016602 y + 0.67969 (bf16 values of the minimax coefficients), low | high halves scaled as above
     asm("{\n\t.reg .b32 u;\n\t"
         "fma.rn.bf16x2 u, %1, %2, %3;\n\t"
         "fma.rn.bf16x2 %0, u, %2, %4;\n\t}"
-        : "=r"(q) : "r"(0x3EAD3EADu), "r"(y), "r"(0xBC88BC88u), "r"(0x3F2E3F2Eu));
-    return q + e - 0x20002000u;
+        : "=r"(q) : "r"(0x16AD5E2Du), "r"(y), "r"(0x9488DC08u), "r"(0x172E5EAEu));
+    return q + w - y;
 }
 __device__ __forceinline__ float sumsq_bf16x2(uint32_t v) {
     const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
