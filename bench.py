@@ -369,7 +369,7 @@ def main():
         roof = {"bound": "tensor", "kernel": f"attn_tc_kernel<hd={64 // heads}> (tcgen05/TMEM bounded-softmax self-attention, full resolution, L={H * Wd})",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 # dram__bytes_read+write of this launch from profiles/r1_attn_tc_ncu_metrics.csv (ncu --set full, same shape)
-                "traffic": 544.6e6 if (fam == "avif" and bsz == 16 and H * Wd == 65536) else None,
+                "traffic": 542.1e6 if (fam == "avif" and bsz == 16 and H * Wd == 65536) else None,
                 "algorithmic_bytes": bsz * H * Wd * 64 * 2 * 4,
                 "peak_source": pk["src"] + " (sustained bf16 GEMM)", "launch_ms": avg_ms,
                 "launches_timed": len(attn), "share_of_step": sum(m for m, _ in attn) / ms,
@@ -378,7 +378,7 @@ def main():
                              "frac": heads * (H * Wd) ** 2 * bsz / (avg_ms * 1e-3) / (16 * 148 * (clk["sm_mhz"] or 1965.0) * 1e6)},
                 "note": "this kernel is bound by the exp (MUFU) + issue pipes, not the tensor pipe: head_dim 8/16 gives 16-32 "
                         "FLOP per exp.  exp_pipe.frac is against the MUFU-only ceiling (16 exp2/clk/SM); the kernel evaluates "
-                        "3 of every 8 exps on the FMA pipe, so it can exceed 1.  See DESIGN.md section 4 and "
+                        "every other score pair on the FMA/ALU pipes (packed bf16), so it can exceed 1.  See DESIGN.md section 4 and "
                         "profiles/r1_ncu_summary.md"}
     unet_tflops = UNET_GF[fam] * B / 1e3 / (ms_per_step / 1e3) if args.res == 256 else None
 
