@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="train workload: one all-reduce after the backward instead of buckets under it")
     ap.add_argument("--projection", default="auto", choices=["auto", "codec", "dct", "device"],
                     help="data-consistency step: auto (default: device JPEG codec for --family jpeg, host codec otherwise), the "
                          "reference's host codec, the bit-exact device JPEG round trip "
@@ -189,7 +190,7 @@ def run_train(args):
     Bn, res = (args.batch if args.batch != 64 else 32), (args.res if args.res != 256 else 64)
     torch.manual_seed(0)
     model = P.WebPDiffusionModel().to(dev).set_precision("bf16")
-    tr = Trainer(model, seed=rank)
+    tr = Trainer(model, seed=rank, overlap_allreduce=not args.no_overlap)
     g = torch.Generator().manual_seed(100 + rank)
     x0 = (torch.rand(Bn, 3, res, res, generator=g) * 2 - 1)
     xt = codec.webp_compress(x0, 30).contiguous().pin_memory()
@@ -219,10 +220,16 @@ def run_train(args):
         dist.barrier()
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
+    sync_err = 0.0
     if world > 1:
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
+        # replicas must still hold identical parameters after K averaged steps (checks the bucketed all-reduce)
+        chk = torch.stack([p.detach().double().abs().sum() for p in model.parameters()]).sum().view(1)
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        sync_err = float((hi - lo) / hi)
     if rank == 0:
         val = world * Bn * K / (ms / 1e3)
         nparam = sum(p.numel() for p in model.parameters())
@@ -230,11 +237,11 @@ def run_train(args):
                           "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                           "config": {"workload": f"webp_training.py training step, WebP UNet {res}x{res}, batch {Bn}/GPU, "
-                                                 "frequency_aware_loss, clip+AdamW, flat fp32 gradient all-reduce (NCCL)",
+                                                 "frequency_aware_loss, clip+AdamW, fp32 gradient all-reduce (NCCL) in " + ("one piece after" if args.no_overlap else "buckets under") + " the backward",
                                      "allreduce_bytes": nparam * 4},
                           "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 2 * xt.numel() * 4 + Bn * 4,
                                   "d2h_bytes_per_step": 4.0 / K},
-                          "gpu_launches": ops.LAUNCHES[0], "clocks": clk, "loss": lossv}), flush=True)
+                          "gpu_launches": ops.LAUNCHES[0], "clocks": clk, "loss": lossv, "replica_param_mismatch": sync_err}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

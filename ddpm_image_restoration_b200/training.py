@@ -24,7 +24,7 @@ F32 = torch.float32
 
 class Trainer:
     def __init__(self, model, lr=2e-4, weight_decay=1e-5, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=1.0, dropout=0.1,
-                 seed=0):
+                 seed=0, overlap_allreduce=True, bucket_bytes=64 << 20):
         if model.family not in ("webp", "jpeg"):
             raise NotImplementedError("training kernels cover the WebP/JPEG families (DCT frequency block) only")
         self.model = model
@@ -44,6 +44,15 @@ class Trainer:
         self.m = {k: torch.zeros_like(p, dtype=F32) for k, p in self.params.items()}
         self.v = {k: torch.zeros_like(p, dtype=F32) for k, p in self.params.items()}
         self._norm_acc = torch.zeros((1,), dtype=torch.float64, device=dev)
+        # gradient buckets for the data-parallel all-reduce: the backward finishes the blocks in reverse registration order,
+        # so every finished block closes a contiguous tail [start(block), previous start) of the flat buffer
+        self.overlap_allreduce, self.bucket_bytes = overlap_allreduce, bucket_bytes
+        self._span_start, off = {}, 0
+        for k, p in self.params.items():
+            owner = ".".join(k.split(".")[:2]) if k.startswith("bottleneck.") else k.split(".")[0]
+            self._span_start.setdefault(owner, off)
+            off += p.numel()
+        self._ar_pending, self._ar_hi = [], n
 
     # ------------------------------------------------------------------------------------------------------------
     def _pack(self):
@@ -95,6 +104,7 @@ class Trainer:
         impl = m.impl
         G = self.grads
         self.flat_grad.zero_()
+        self._ar_pending, self._ar_hi = [], self.flat_grad.numel()
         xt = xt.contiguous().float(); x0 = x0.contiguous().float(); t = t.contiguous().float()
         B = xt.shape[0]
         p_drop = self.dropout_p
@@ -144,7 +154,9 @@ class Trainer:
             dt_emb = torch.zeros_like(t_emb)
 
             def bwd(p, dout):
-                return self._block_bwd(p, dout, tapes.pop(p), t_emb, dt_emb, boost, sd, P[p], dt, impl, p_drop)
+                r = self._block_bwd(p, dout, tapes.pop(p), t_emb, dt_emb, boost, sd, P[p], dt, impl, p_drop)
+                self._grads_final_from(self._span_start[p])
+                return r
             dcat = bwd("up5", du5)
             du4, dd1 = T.upsample2_concat_backward(dcat, 64)
             dcat = bwd("up4", du4)
@@ -302,10 +314,30 @@ class Trainer:
                                     G[f"{p}.norm1.weight"], G[f"{p}.norm1.bias"], dx=dx, accumulate=True)
 
     # ------------------------------------------------------------------------------------------------------------
+    def _grads_final_from(self, lo):
+        """Called by the backward when every gradient at offsets >= lo is final.  With several ranks the finished tail is
+        all-reduced right away in buckets of >= bucket_bytes (NCCL runs them on its own stream, ordered after the kernels
+        enqueued so far), so the collective overlaps the rest of the backward."""
+        import torch.distributed as dist
+        if not (self.overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if (self._ar_hi - lo) * 4 >= self.bucket_bytes:
+            self._ar_pending.append(dist.all_reduce(self.flat_grad[lo:self._ar_hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._ar_hi = lo
+
     def allreduce_grads(self):
-        """Data-parallel gradient averaging: one NCCL all-reduce of the flat gradient buffer."""
-        from .parallel import allreduce_mean_
-        allreduce_mean_(self.flat_grad)
+        """Data-parallel gradient averaging over NCCL: whatever the backward has not already sent in buckets goes out as
+        one more all-reduce of the head of the flat buffer; then one scale by 1 / world."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        if self._ar_hi > 0:
+            self._ar_pending.append(dist.all_reduce(self.flat_grad[:self._ar_hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._ar_hi = 0
+        for h in self._ar_pending:
+            h.wait()
+        self._ar_pending = []
+        self.flat_grad.mul_(1.0 / dist.get_world_size())
 
     def optimizer_step(self):
         """clip_grad_norm_(max_grad_norm) + AdamW, webp_training.py:522-524."""
