@@ -74,9 +74,14 @@ __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
 //   r = q + w - y (one IADD3 on the whole word) lands on q * 2^(N - 64) in both halves: the fraction bits of w and y cancel,
 //       the exponent offsets (63 - 127 + 0 and -80 - 127 + 143) both come to -64.
 __device__ __forceinline__ uint32_t ex2_pair_bf16(float x0, float x1) {
-    const float K = 65600.f;
-    const uint32_t t0 = __float_as_uint(x0 + K), t1 = __float_as_uint(x1 + K);
-    uint32_t w, q;
+    uint32_t t0, t1, w, q;
+    // both magic adds in one packed fp32 instruction (sm_100 add.f32x2 on a 64-bit register pair)
+    asm("{\n\t.reg .b64 xx, kk, tt;\n\t"
+        "mov.b64 xx, {%2, %3};\n\t"
+        "mov.b64 kk, {%4, %4};\n\t"
+        "add.rn.f32x2 tt, xx, kk;\n\t"
+        "mov.b64 {%0, %1}, tt;\n\t}"
+        : "=r"(t0), "=r"(t1) : "f"(x0), "f"(x1), "f"(65600.f));
     asm("mad.lo.u32 %0, %1, 65536, %2;\n" : "=r"(w) : "r"(t1), "r"(t0));
     uint32_t y;            // (w & 0x007F007F) | 0x3F803F80 as ONE lop3: both masks must be register operands for that
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;\n" : "=r"(y) : "r"(w), "r"(0x007F007Fu), "r"(0x3F803F80u));
