@@ -204,8 +204,15 @@ class _RestorationUNet(nn.Module):
                 q["q2_w"] = lin(sd[f"{a}.quantization.2.weight"])
                 q["c0_w"] = lin(sd[f"{f}.color_consistency.0.weight"])
                 q["c2_w"] = lin(sd[f"{f}.color_consistency.2.weight"])
-                q["e0_w"] = conv3(sd[f"{f}.edge_preserve.0.weight"])
-                q["e2_w"] = conv3(sd[f"{f}.edge_preserve.2.weight"])
+                # edge_preserve: C -> C/2 -> C.  At C = 64 the hidden width (32) is below the tcgen05 kernel's 64-wide K block, so
+                # the hidden layer is zero-padded to 64 channels: relu(0 * x + 0) = 0 feeds zero weights, the result is identical
+                w0, b0, w2 = sd[f"{f}.edge_preserve.0.weight"], f32(sd[f"{f}.edge_preserve.0.bias"]), sd[f"{f}.edge_preserve.2.weight"]
+                if dt == torch.bfloat16 and w0.shape[0] < 64:
+                    padn = 64 - w0.shape[0]
+                    w0 = torch.cat([w0, w0.new_zeros(padn, *w0.shape[1:])], 0)
+                    b0 = torch.cat([b0, b0.new_zeros(padn)], 0)
+                    w2 = torch.cat([w2, w2.new_zeros(w2.shape[0], padn, 3, 3)], 1)
+                q["e0_w"], q["e0_b"], q["e2_w"] = conv3(w0), b0.contiguous(), conv3(w2)
                 for i in range(4):
                     q[f"ms{i}_w1"] = f32(sd[f"{f}.multi_scale_attn.{i}.1.weight"].reshape(co // 4, co))
                     q[f"ms{i}_w3"] = f32(sd[f"{f}.multi_scale_attn.{i}.3.weight"].reshape(co, co // 4))
@@ -334,7 +341,7 @@ class _RestorationUNet(nn.Module):
             c1 = ops.gemm(h3_op, W["c0_w"], co, impl, bias=sd[f"{f}.color_consistency.0.bias"], act=ops.ACT_RELU)
             color = ops.gemm(c1, W["c2_w"], co, impl, bias=sd[f"{f}.color_consistency.2.bias"], act=ops.ACT_SIGMOID,
                              img_scale=boosts[0])
-            e1 = ops.conv3x3(h3_op, W["e0_w"], co // 2, impl, bias=sd[f"{f}.edge_preserve.0.bias"], act=ops.ACT_RELU)
+            e1 = ops.conv3x3(h3_op, W["e0_w"], W["e0_b"].shape[0], impl, bias=W["e0_b"], act=ops.ACT_RELU)
             edge = ops.conv3x3(e1, W["e2_w"], co, impl, bias=sd[f"{f}.edge_preserve.2.bias"], act=ops.ACT_SIGMOID,
                                img_scale=boosts[1])
             e = ops.avif_combine(h3, xt, gates, color, edge)
