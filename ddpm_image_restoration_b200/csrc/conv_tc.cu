@@ -24,6 +24,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int STREAM_THREADS = 320;   // persistent kernel: eight epilogue warps (2..9), two per TMEM lane quarter, each taking
+                                      // half of the output columns -- the epilogue is bound by loads in flight per SM
 
 struct TcParams {
     long long M;
@@ -149,7 +151,7 @@ struct StreamParams {
 };
 
 template <int TCOLS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
 igemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        void* __restrict__ out, EpiDev ep, StreamParams sp) {
     const TcParams& p = sp.t;
@@ -174,7 +176,7 @@ igemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tma_prefetch_desc(&tmap_b);
         mbar_init(w_full, 1);
         for (int s = 0; s < sp.a_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
@@ -240,8 +242,11 @@ igemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             EpiRow row;
             if (m_ok) row = epi_row(ep, m);
             const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * (TCOLS / 2));
+            // warps 2..5 take the first half of the columns, warps 6..9 the second (whole 16-column chunks)
+            const int chunks = p.N / 16, c_split = ((chunks + 1) / 2) * 16;
+            const int c_lo = warp < 6 ? 0 : c_split, c_hi = warp < 6 ? c_split : p.N;
 #pragma unroll 1
-            for (int c0 = 0; c0 < p.N; c0 += 16) {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
                 float v[16];
                 tmem_ld16(t_addr + (uint32_t)c0, v);
                 if (m_ok) epi_chunk16(ep, row, v, m, c0, out);
@@ -283,7 +288,7 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const
         if (e != cudaSuccess) { ddpmir_set_error("igemm_tc_stream: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
         attr_smem = smem;
     }
-    igemm_tc_stream_kernel<TCOLS><<<grid, NUM_THREADS, smem, st>>>(ta, tb, out, ep, sp);
+    igemm_tc_stream_kernel<TCOLS><<<grid, STREAM_THREADS, smem, st>>>(ta, tb, out, ep, sp);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
