@@ -24,8 +24,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
-constexpr int STREAM_THREADS = 320;   // persistent kernel: eight epilogue warps (2..9), two per TMEM lane quarter, each taking
-                                      // half of the output columns -- the epilogue is bound by loads in flight per SM
+constexpr int STREAM_EPI_GROUPS = 4;   // persistent kernel: 4 x 4 epilogue warps (2..17), four per TMEM lane quarter, each group
+constexpr int STREAM_THREADS = (2 + 4 * STREAM_EPI_GROUPS) * 32;   // taking a share of the output columns -- the epilogue is bound
+                                      // by loads in flight per SM
 
 struct TcParams {
     long long M;
@@ -176,7 +177,7 @@ igemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tma_prefetch_desc(&tmap_b);
         mbar_init(w_full, 1);
         for (int s = 0; s < sp.a_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4 * STREAM_EPI_GROUPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
@@ -242,9 +243,9 @@ igemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             EpiRow row;
             if (m_ok) row = epi_row(ep, m);
             const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * (TCOLS / 2));
-            // warps 2..5 take the first half of the columns, warps 6..9 the second (whole 16-column chunks)
-            const int chunks = p.N / 16, c_split = ((chunks + 1) / 2) * 16;
-            const int c_lo = warp < 6 ? 0 : c_split, c_hi = warp < 6 ? c_split : p.N;
+            // epilogue group (warp - 2) / 4 takes its share of the 16-column chunks
+            const int chunks = p.N / 16, per = (chunks + STREAM_EPI_GROUPS - 1) / STREAM_EPI_GROUPS, grp = (warp - 2) >> 2;
+            const int c_lo = min(p.N, grp * per * 16), c_hi = min(p.N, (grp + 1) * per * 16);
 #pragma unroll 1
             for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
                 float v[16];
