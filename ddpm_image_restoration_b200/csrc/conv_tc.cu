@@ -23,7 +23,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int EPI_GROUPS = 2;      // epilogue warp groups of four (one warp per TMEM lane quarter); each takes a share of the columns
+constexpr int NUM_THREADS = (2 + 4 * EPI_GROUPS) * 32;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then the epilogue warps
 constexpr int STREAM_EPI_GROUPS = 4;   // persistent kernel: 4 x 4 epilogue warps (2..17), four per TMEM lane quarter, each group
 constexpr int STREAM_THREADS = (2 + 4 * STREAM_EPI_GROUPS) * 32;   // taking a share of the output columns -- the epilogue is bound
                                       // by loads in flight per SM
@@ -115,8 +116,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const bool m_ok = m < p.M;
         EpiRow row;
         if (m_ok) row = epi_row(ep, m);
+        constexpr int PER = (BLOCK_N / 16 + EPI_GROUPS - 1) / EPI_GROUPS * 16;     // columns per epilogue group
+        const int grp = (warp - 2) >> 2;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        for (int c0 = grp * PER; c0 < min(BLOCK_N, (grp + 1) * PER); c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
             if (m_ok) {
