@@ -22,6 +22,18 @@ from .models import _BLOCKS, _FAMILY, _groups
 F32 = torch.float32
 
 
+def grad_span_starts(model):
+    """Offset, in the flat gradient buffer (parameters in registration order), at which each top-level block's parameters
+    start: {"time_embed": 0, "down1": ..., "bottleneck.0": ..., "out_conv": ...}.  The backward finishes blocks in reverse
+    registration order, so "everything from span_start[block] on is final" holds after each block."""
+    spans, off = {}, 0
+    for k, p in model.named_parameters():
+        owner = ".".join(k.split(".")[:2]) if k.startswith("bottleneck.") else k.split(".")[0]
+        spans.setdefault(owner, off)
+        off += p.numel()
+    return spans
+
+
 class Trainer:
     def __init__(self, model, lr=2e-4, weight_decay=1e-5, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=1.0, dropout=0.1,
                  seed=0, overlap_allreduce=True, bucket_bytes=64 << 20):
@@ -47,11 +59,7 @@ class Trainer:
         # gradient buckets for the data-parallel all-reduce: the backward finishes the blocks in reverse registration order,
         # so every finished block closes a contiguous tail [start(block), previous start) of the flat buffer
         self.overlap_allreduce, self.bucket_bytes = overlap_allreduce, bucket_bytes
-        self._span_start, off = {}, 0
-        for k, p in self.params.items():
-            owner = ".".join(k.split(".")[:2]) if k.startswith("bottleneck.") else k.split(".")[0]
-            self._span_start.setdefault(owner, off)
-            off += p.numel()
+        self._span_start = grad_span_starts(model)
         self._ar_pending, self._ar_hi = [], n
 
     # ------------------------------------------------------------------------------------------------------------

@@ -22,6 +22,30 @@ def test_checkpoint_layout(fam, cls, n):
     assert sum(p.numel() for p in m.parameters()) == {"webp": 114398409, "jpeg": 114398409, "avif": 158284137}[fam]
 
 
+def test_gradient_bucket_spans_follow_backward_order():
+    """The bucketed all-reduce relies on the flat gradient buffer being laid out in registration order, so that the blocks
+    the backward finishes (out_conv, up5 ... down1, time_embed) close contiguous tails of it."""
+    import ddpm_image_restoration_b200 as P
+    from ddpm_image_restoration_b200.training import grad_span_starts
+    m = P.WebPDiffusionModel()
+    spans = grad_span_starts(m)
+    order = ["time_embed", "down1", "down2", "down3", "down4", "down5", "bottleneck.0", "bottleneck.1", "bottleneck.2",
+             "up1", "up2", "up3", "up4", "up5", "out_conv"]
+    assert list(spans) == order and spans["time_embed"] == 0
+    starts = [spans[k] for k in order]
+    assert starts == sorted(starts) and len(set(starts)) == len(starts)
+    total = sum(p.numel() for p in m.parameters())
+    assert starts[-1] < total
+    # every parameter of a block lies inside [start(block), start(next block))
+    off = 0
+    for k, p in m.named_parameters():
+        owner = ".".join(k.split(".")[:2]) if k.startswith("bottleneck.") else k.split(".")[0]
+        i = order.index(owner)
+        hi = starts[i + 1] if i + 1 < len(starts) else total
+        assert starts[i] <= off and off + p.numel() <= hi
+        off += p.numel()
+
+
 def test_checkpoint_layout_m0409():
     """0409 notebook's JPEGDiffusionModel: 282 entries, 119 873 161 parameters."""
     from ddpm_image_restoration_b200 import method0409
