@@ -11,9 +11,8 @@ without its lossless entropy coder.  Restated from the library's published algor
   jdsample.c  h2v2_fancy_upsample (triangle filter, replicated edges)           -> up_h2v2_fancy
   jdcolor.c   ycc_rgb_convert                                                   -> ycc2rgb
 Pinned: bit-exact against Pillow's own round trip for every quality and both subsampling modes on noise, smooth and
-hard-edged images (tests/test_oracle.py::test_jpeg_exact_restatement_vs_pillow).  Sizes must be multiples of 16 (4:2:0)
-or 8 (4:4:4): MCU edge padding is not restated.  The GPU kernels (csrc/jpeg_exact.cu) are checked against this file and
-against Pillow.
+hard-edged images of arbitrary size (tests/test_oracle.py::test_jpeg_exact_restatement_vs_pillow), MCU edge padding
+included.  The GPU kernels (csrc/jpeg_exact.cu) cover sizes without padding and are checked against this file and Pillow.
 """
 import io, numpy as np
 from PIL import Image
@@ -115,12 +114,33 @@ def up_h2v2_fancy(p):
     return out
 
 def roundtrip_rgb(img, quality, sub420):
-    qy,qc=qtables(quality)
-    y,cb,cr=rgb2ycc(img)
-    if sub420: cb,cr=down_h2v2(cb),down_h2v2(cr)
-    y=plane_roundtrip(y,qy); cb=plane_roundtrip(cb,qc); cr=plane_roundtrip(cr,qc)
-    if sub420: cb,cr=up_h2v2_fancy(cb),up_h2v2_fancy(cr)
-    return ycc2rgb(y,cb,cr).astype(np.uint8)
+    """img: [H, W, 3] uint8, any size.  Sizes that are not a multiple of the MCU (16 with 4:2:0, 8 with 4:4:4) are padded the
+    way libjpeg does it: the encoder replicates the last row / column of the colour-converted planes up to the MCU boundary
+    (jcprepct.c expand_bottom_edge, jcsample.c expand_right_edge); the decoder upsamples and colour-converts only the real
+    ceil(H/2) x ceil(W/2) chroma samples (edge cases of the triangle filter at the REAL edge) and crops to H x W."""
+    H, W = img.shape[:2]
+    mcu = 16 if sub420 else 8
+    Hp, Wp = -(-H // mcu) * mcu, -(-W // mcu) * mcu
+    qy, qc = qtables(quality)
+    y, cb, cr = rgb2ycc(img)
+    # columns: replicated at full resolution up to the MCU boundary BEFORE downsampling (jcsample.c expand_right_edge);
+    # rows: full resolution only up to a multiple of the vertical sampling factor (jcprepct.c), then every component's
+    # (downsampled) plane is padded to the iMCU height by replicating ITS last row (expand_bottom_edge on the output)
+    He = H + (H & 1) if sub420 else H
+    padw = lambda p: np.pad(p, ((0, He - H), (0, Wp - W)), mode="edge")
+    y, cb, cr = padw(y), padw(cb), padw(cr)
+    if sub420:
+        cb, cr = down_h2v2(cb), down_h2v2(cr)
+    padh = lambda p, rows: np.pad(p, ((0, rows - p.shape[0]), (0, 0)), mode="edge")
+    y = padh(y, Hp)
+    cb, cr = padh(cb, Hp // 2 if sub420 else Hp), padh(cr, Hp // 2 if sub420 else Hp)
+    y = plane_roundtrip(y, qy); cb = plane_roundtrip(cb, qc); cr = plane_roundtrip(cr, qc)
+    if sub420:
+        ch, cw = -(-H // 2), -(-W // 2)
+        # jdsample.c jinit_upsampler: the triangle filter is only used when the downsampled width exceeds 2, else replication
+        up = up_h2v2_fancy if cw > 2 else (lambda p: np.repeat(np.repeat(p, 2, axis=0), 2, axis=1))
+        cb, cr = up(cb[:ch, :cw]), up(cr[:ch, :cw])
+    return ycc2rgb(y[:H, :W], cb[:H, :W], cr[:H, :W]).astype(np.uint8)
 
 def pil_roundtrip(img, quality, mode, sub=None):
     buf=io.BytesIO(); kw={}

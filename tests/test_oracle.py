@@ -150,8 +150,11 @@ def test_jpeg_exact_restatement_vs_pillow():
     """oracle/jpeg_exact.py (libjpeg-turbo's integer pipeline restated) against Pillow's own JPEG round trip: bit-exact."""
     from oracle import jpeg_exact as J
     rng = np.random.default_rng(5)
-    for trial in range(12):
-        H, W = 16 * int(rng.integers(1, 4)), 16 * int(rng.integers(1, 5))
+    for trial in range(18):
+        if trial < 12:
+            H, W = 16 * int(rng.integers(1, 4)), 16 * int(rng.integers(1, 5))
+        else:       # sizes that need MCU edge padding, down to widths the decoder upsamples by replication
+            H, W = int(rng.integers(1, 50)), int(rng.integers(1, 60)) if trial % 2 else int(rng.integers(1, 6))
         if trial % 3 == 0:
             img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
         elif trial % 3 == 1:
