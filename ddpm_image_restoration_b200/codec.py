@@ -98,11 +98,8 @@ def _compress(x, quality, codec):
     if x.is_cuda:
         u8 = ops.quantize_u8_hwc(x.contiguous().float())
         if codec == "jpeg":
-            q = _clamp_quality(codec, quality)
-            mcu = 16 if q <= 30 else 8
-            if x.shape[2] % mcu == 0 and x.shape[3] % mcu == 0:
-                # same bytes as the Pillow round trip below (ddpmir_jpeg_roundtrip_u8), without leaving the device
-                return ops.u8_hwc_to_nchw(ops.jpeg_roundtrip_u8(u8, q))
+            # same bytes as the Pillow round trip below (ddpmir_jpeg_roundtrip_u8), without leaving the device
+            return ops.u8_hwc_to_nchw(ops.jpeg_roundtrip_u8(u8, _clamp_quality(codec, quality)))
         host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(u8, non_blocking=True)
         torch.cuda.current_stream().synchronize()

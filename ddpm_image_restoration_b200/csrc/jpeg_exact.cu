@@ -8,7 +8,7 @@
 //   decoder: dequantise + jpeg_idct_islow (jidctint.c), "fancy" triangle-filter h2v2 upsampling (jdsample.c),
 //            YCbCr -> RGB (jdcolor.c).
 // oracle/jpeg_exact.py restates the same pipeline in numpy and is pinned bit-exactly against Pillow over all qualities.
-// Image sizes must be multiples of 16 (4:2:0) or 8 (4:4:4), so no MCU edge padding is involved.
+// Any image size: planes are padded to whole MCUs (16 with 4:2:0, 8 with 4:4:4) the way libjpeg pads them.
 #include "common.cuh"
 #include <stdint.h>
 
@@ -71,32 +71,46 @@ inline int grid_for(long long total, int block) {
     return (int)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g));
 }
 
-// RGB (uint8 HWC) -> Y plane and (optionally 2x2 downsampled) Cb / Cr planes.  One thread per 2x2 pixel quad.
+// RGB (uint8 HWC, H x W) -> Y plane (Hp x Wp) and Cb / Cr planes (Hp x Wp, or Hp/2 x Wp/2 when SUB), Hp / Wp = size rounded up
+// to the MCU.  One thread per 2x2 quad of the PADDED image.  Padding as libjpeg does it: columns are replicated at full
+// resolution before downsampling (jcsample.c expand_right_edge); rows are replicated at full resolution only up to an even
+// height, beyond that every plane repeats ITS last row (jcprepct.c expand_bottom_edge on the downsampled output).
 template <bool SUB>
 __global__ void __launch_bounds__(256)
 rgb_to_ycc_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ yp, uint8_t* __restrict__ cbp, uint8_t* __restrict__ crp,
-                  int H, int W, long long total) {
+                  int H, int W, int Hp, int Wp, long long total) {
     constexpr int FIX_299 = 19595, FIX_587 = 38470, FIX_114 = 7471, FIX_16874 = 11059, FIX_33126 = 21709, FIX_5 = 32768,
                   FIX_41869 = 27439, FIX_08131 = 5329, HALF = 1 << 15, OFF = 128 << 16;
-    const int W2 = W >> 1, H2 = H >> 1;
+    const int W2 = Wp >> 1, H2 = Hp >> 1, ch = (H + 1) >> 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int qx = (int)(i % W2);
         long long r = i / W2;
         const int qy = (int)(r % H2);
         const long long b = r / H2;
+        const uint8_t* img = rgb + b * H * W * 3;
         int cbs = 0, crs = 0;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-                const int y = 2 * qy + dy, x = 2 * qx + dx;
-                const uint8_t* p = rgb + ((b * H + y) * W + x) * 3;
-                const int R = p[0], G = p[1], B = p[2];
-                yp[(b * H + y) * W + x] = (uint8_t)((FIX_299 * R + FIX_587 * G + FIX_114 * B + HALF) >> 16);
-                const int cb = (-FIX_16874 * R - FIX_33126 * G + FIX_5 * B + OFF + HALF - 1) >> 16;
-                const int cr = (FIX_5 * R - FIX_41869 * G - FIX_08131 * B + OFF + HALF - 1) >> 16;
-                if (SUB) { cbs += cb; crs += cr; }
-                else { cbp[(b * H + y) * W + x] = (uint8_t)cb; crp[(b * H + y) * W + x] = (uint8_t)cr; }
+                const int yo = 2 * qy + dy, xo = 2 * qx + dx;                 // position in the padded planes
+                const int x = min(xo, W - 1);
+                {
+                    const uint8_t* p = img + ((long long)min(yo, H - 1) * W + x) * 3;
+                    const int R = p[0], G = p[1], B = p[2];
+                    yp[(b * Hp + yo) * Wp + xo] = (uint8_t)((FIX_299 * R + FIX_587 * G + FIX_114 * B + HALF) >> 16);
+                    if (!SUB) {
+                        cbp[(b * Hp + yo) * Wp + xo] = (uint8_t)((-FIX_16874 * R - FIX_33126 * G + FIX_5 * B + OFF + HALF - 1) >> 16);
+                        crp[(b * Hp + yo) * Wp + xo] = (uint8_t)((FIX_5 * R - FIX_41869 * G - FIX_08131 * B + OFF + HALF - 1) >> 16);
+                    }
+                }
+                if (SUB) {      // chroma quad: rows of the last REAL chroma row when this quad lies below the image
+                    const int yc = min(2 * min(qy, ch - 1) + dy, H - 1);
+                    const uint8_t* p = img + ((long long)yc * W + x) * 3;
+                    const int R = p[0], G = p[1], B = p[2];
+                    cbs += (-FIX_16874 * R - FIX_33126 * G + FIX_5 * B + OFF + HALF - 1) >> 16;
+                    crs += (FIX_5 * R - FIX_41869 * G - FIX_08131 * B + OFF + HALF - 1) >> 16;
+                }
             }
         if (SUB) {
             const int bias = (qx & 1) ? 2 : 1;       // jcsample.c h2v2_downsample: bias = 1, 2, 1, 2, ... along the row
@@ -171,11 +185,13 @@ block_roundtrip_kernel(uint8_t* __restrict__ planes, long long nblk_y, int ybw, 
     }
 }
 
-// decoded planes -> RGB uint8 HWC; SUB: chroma is half resolution and goes through jdsample.c's h2v2 fancy upsampling
+// decoded planes (padded, see above) -> RGB uint8 HWC of the real H x W image; SUB: chroma is half resolution and goes through
+// jdsample.c's h2v2 fancy upsampling over the REAL ceil(H/2) x ceil(W/2) samples (edge cases at the real edge), or through
+// plain replication when the real chroma width is <= 2 (jinit_upsampler)
 template <bool SUB>
 __global__ void __launch_bounds__(256)
 ycc_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ cbp, const uint8_t* __restrict__ crp,
-                  uint8_t* __restrict__ rgb, int H, int W, long long total) {
+                  uint8_t* __restrict__ rgb, int H, int W, int Hp, int Wp, long long total) {
     constexpr int FIX_1402 = 91881, FIX_1772 = 116130, FIX_71414 = 46802, FIX_34414 = 22554, HALF = 1 << 15;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W);
@@ -184,15 +200,16 @@ ycc_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ cb
         const long long b = r / H;
         int cb, cr;
         if (SUB) {
-            const int W2 = W >> 1, H2 = H >> 1;
+            const int W2 = Wp >> 1, H2 = Hp >> 1, cw = (W + 1) >> 1, chh = (H + 1) >> 1;
             const int cy = y >> 1, cx = x >> 1;
-            const int fy = (y & 1) ? min(cy + 1, H2 - 1) : max(cy - 1, 0);      // the farther of the two nearest chroma rows
+            const int fy = (y & 1) ? min(cy + 1, chh - 1) : max(cy - 1, 0);      // the farther of the two nearest chroma rows
             auto up = [&](const uint8_t* pl) {
                 const uint8_t* near = pl + (b * H2 + cy) * W2;
+                if (cw <= 2) return (int)near[cx];
                 const uint8_t* far = pl + (b * H2 + fy) * W2;
                 const int cs = 3 * near[cx] + far[cx];                                   // thiscolsum
                 if (x & 1) {
-                    if (cx == W2 - 1) return (cs * 4 + 7) >> 4;
+                    if (cx == cw - 1) return (cs * 4 + 7) >> 4;
                     return (3 * cs + (3 * near[cx + 1] + far[cx + 1]) + 7) >> 4;
                 }
                 if (cx == 0) return (cs * 4 + 8) >> 4;
@@ -200,9 +217,9 @@ ycc_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ cb
             };
             cb = up(cbp); cr = up(crp);
         } else {
-            cb = cbp[i]; cr = crp[i];
+            cb = cbp[(b * Hp + y) * Wp + x]; cr = crp[(b * Hp + y) * Wp + x];
         }
-        const int Y = yp[i], xb = cb - 128, xr = cr - 128;
+        const int Y = yp[(b * Hp + y) * Wp + x], xb = cb - 128, xr = cr - 128;
         const int R = Y + ((FIX_1402 * xr + HALF) >> 16);
         const int B = Y + ((FIX_1772 * xb + HALF) >> 16);
         const int G = Y + ((-FIX_34414 * xb + HALF - FIX_71414 * xr) >> 16);
@@ -213,16 +230,15 @@ ycc_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ cb
 
 }  // namespace
 
-extern "C" size_t ddpmir_jpeg_roundtrip_workspace(int B, int H, int W) { return (size_t)B * H * W * 3; }
+extern "C" size_t ddpmir_jpeg_roundtrip_workspace(int B, int H, int W) {
+    return (size_t)B * ((H + 15) / 16 * 16) * ((W + 15) / 16 * 16) * 3;
+}
 
 extern "C" int ddpmir_jpeg_roundtrip_u8(const uint8_t* rgb, uint8_t* out, int B, int H, int W, int quality, int subsample_420,
                                         void* workspace, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(rgb && out && workspace && B > 0 && H > 0 && W > 0, "jpeg_roundtrip: bad arguments");
     const int mcu = subsample_420 ? 16 : 8;
-    if (H % mcu != 0 || W % mcu != 0) {
-        ddpmir_set_error("jpeg_roundtrip: H and W must be multiples of %d (use the host codec otherwise)", mcu);
-        return DDPMIR_ERR_UNSUPPORTED;
-    }
+    const int Hp = (H + mcu - 1) / mcu * mcu, Wp = (W + mcu - 1) / mcu * mcu;       // planes padded to whole MCUs
     static const int QY[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56,
                                14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92,
                                49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
@@ -240,22 +256,22 @@ extern "C" int ddpmir_jpeg_roundtrip_u8(const uint8_t* rgb, uint8_t* out, int B,
     }
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)workspace;
-    const long long y_bytes = (long long)B * H * W;
-    const int cH = subsample_420 ? H / 2 : H, cW = subsample_420 ? W / 2 : W;
+    const long long y_bytes = (long long)B * Hp * Wp;
+    const int cH = subsample_420 ? Hp / 2 : Hp, cW = subsample_420 ? Wp / 2 : Wp;
     const long long c_bytes = (long long)B * cH * cW;
     uint8_t *yp = ws, *cbp = ws + y_bytes, *crp = cbp + c_bytes;
-    const long long quads = (long long)B * (H / 2) * (W / 2);
-    if (subsample_420) rgb_to_ycc_kernel<true><<<grid_for(quads, 256), 256, 0, st>>>(rgb, yp, cbp, crp, H, W, quads);
-    else rgb_to_ycc_kernel<false><<<grid_for(quads, 256), 256, 0, st>>>(rgb, yp, cbp, crp, H, W, quads);
+    const long long quads = (long long)B * (Hp / 2) * (Wp / 2);
+    if (subsample_420) rgb_to_ycc_kernel<true><<<grid_for(quads, 256), 256, 0, st>>>(rgb, yp, cbp, crp, H, W, Hp, Wp, quads);
+    else rgb_to_ycc_kernel<false><<<grid_for(quads, 256), 256, 0, st>>>(rgb, yp, cbp, crp, H, W, Hp, Wp, quads);
     DDPMIR_LAUNCH_CHECK();
-    const long long nblk_y = (long long)B * (H / 8) * (W / 8), nblk_c = (long long)B * (cH / 8) * (cW / 8);
+    const long long nblk_y = (long long)B * (Hp / 8) * (Wp / 8), nblk_c = (long long)B * (cH / 8) * (cW / 8);
     const long long nblk = nblk_y + 2 * nblk_c;
     DDPMIR_CHECK_ARG((nblk + 31) / 32 <= 2147483647LL, "jpeg_roundtrip: too many blocks");
-    block_roundtrip_kernel<<<(unsigned)((nblk + 31) / 32), 256, 0, st>>>(ws, nblk_y, W / 8, W, nblk_c, cW / 8, cW, y_bytes, c_bytes, T);
+    block_roundtrip_kernel<<<(unsigned)((nblk + 31) / 32), 256, 0, st>>>(ws, nblk_y, Wp / 8, Wp, nblk_c, cW / 8, cW, y_bytes, c_bytes, T);
     DDPMIR_LAUNCH_CHECK();
     const long long px = (long long)B * H * W;
-    if (subsample_420) ycc_to_rgb_kernel<true><<<grid_for(px, 256), 256, 0, st>>>(yp, cbp, crp, out, H, W, px);
-    else ycc_to_rgb_kernel<false><<<grid_for(px, 256), 256, 0, st>>>(yp, cbp, crp, out, H, W, px);
+    if (subsample_420) ycc_to_rgb_kernel<true><<<grid_for(px, 256), 256, 0, st>>>(yp, cbp, crp, out, H, W, Hp, Wp, px);
+    else ycc_to_rgb_kernel<false><<<grid_for(px, 256), 256, 0, st>>>(yp, cbp, crp, out, H, W, Hp, Wp, px);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

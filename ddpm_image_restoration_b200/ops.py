@@ -113,7 +113,7 @@ def channel_scale_add(x, y, s, out2_dtype=None):
 
 def jpeg_roundtrip_u8(rgb_u8, quality, out=None):
     """Bit-exact device version of the Pillow JPEG round trip of jpeg_compress (svd.ipynb#c1:L20-44): uint8 [B,H,W,3] in
-    and out, 4:4:4 above quality 30 and 4:2:0 otherwise.  Raises DdpmirError for sizes that need MCU edge padding."""
+    and out (any size), 4:4:4 above quality 30 and 4:2:0 otherwise."""
     if rgb_u8.dtype != torch.uint8 or rgb_u8.dim() != 4 or rgb_u8.shape[-1] != 3:
         raise _lib.DdpmirError("jpeg_roundtrip_u8 needs a uint8 [B,H,W,3] tensor")
     B, H, W, _ = rgb_u8.shape

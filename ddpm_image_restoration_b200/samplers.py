@@ -31,7 +31,7 @@ class _DDRMSampler:
     family = None
 
     def __init__(self, model, seed=0, micro_batches=None, noise_fn=None, projection="auto"):
-        """projection: "auto" (default) = "device" where it exists (JPEG family, sizes without MCU edge padding), else
+        """projection: "auto" (default) = "device" where it exists (JPEG family), else
         "codec"; "codec" = the reference's host codec round trip (Pillow); "device" = JPEG family only: the same
         round trip computed on the GPU with libjpeg-turbo's integer arithmetic (ddpmir_jpeg_roundtrip_u8) -- bit-identical
         pixels, no host hop; "dct" = opt-in DCT-domain projection as the reference's DCTProcessor defines it
@@ -68,9 +68,7 @@ class _DDRMSampler:
         use_phase = quality < cfg["q_thr"]
         projection = self.projection
         if projection == "auto":
-            q = max(1, min(100, int(quality)))
-            mcu = 16 if q <= 30 else 8                      # jpeg_compress: 4:2:0 up to quality 30, 4:4:4 above
-            projection = "device" if (self.family == "jpeg" and H % mcu == 0 and W % mcu == 0) else "codec"
+            projection = "device" if self.family == "jpeg" else "codec"
         st = dict(projection=projection, cfg=cfg, x_t=x_t, x_alt=torch.empty_like(x_t), y=x_t.clone(), quality=quality, steps=steps, eta=eta, eta_b=eta_b,
                   chunks=chunks, use_phase=use_phase, h2d=0, d2h=0, codec_s=0.0, pending=[None] * len(chunks),
                   phasor=ops.phase_reference(x_t) if (use_phase and steps > cfg["period"]) else None)

@@ -242,8 +242,8 @@ int ddpmir_channel_scale_add(const float* x, const float* y, const float* s, int
  * `img.save(buf, "JPEG", quality=q, subsampling=4:4:4 if q > 30 else 4:2:0)` + `Image.open(buf)` -- jpeg_compress,
  * svd.ipynb#c1:L20-44 / 0409_method.ipynb#c0:L44-62 -- computed with libjpeg-turbo's integer arithmetic (colour
  * conversion, h2v2 downsampling, islow DCT, quantisation, islow IDCT, fancy upsampling), entropy coding skipped because
- * it is lossless.  rgb, out: uint8 [B, H, W, 3]; H and W multiples of 16 (4:2:0) or 8 (4:4:4), else
- * DDPMIR_ERR_UNSUPPORTED (callers keep the host codec).  workspace: ddpmir_jpeg_roundtrip_workspace(B, H, W) bytes. */
+ * it is lossless.  rgb, out: uint8 [B, H, W, 3], any H and W (planes are padded to whole MCUs as libjpeg pads them).
+ * workspace: ddpmir_jpeg_roundtrip_workspace(B, H, W) bytes. */
 size_t ddpmir_jpeg_roundtrip_workspace(int B, int H, int W);
 int ddpmir_jpeg_roundtrip_u8(const uint8_t* rgb, uint8_t* out, int B, int H, int W, int quality, int subsample_420,
                              void* workspace, ddpmir_stream_t stream);
