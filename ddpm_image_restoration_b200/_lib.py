@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_uint
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libddpmir.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_SIGMOID, ACT_SILU, ACT_GELU, ACT_TANH = range(7)
 IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR = 0, 1, 2
 
@@ -56,6 +56,8 @@ _SIGNATURES = {
     "ddpmir_jpeg_dct_project": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P]),
     "ddpmir_attention_prescaled_workspace": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "ddpmir_attention_prescaled": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ddpmir_attention_prescaled_f16_workspace": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
+    "ddpmir_attention_prescaled_f16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "ddpmir_block_transform": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "ddpmir_maxpool2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_upsample2_concat": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -82,6 +84,9 @@ _SIGNATURES = {
     "ddpmir_mse_backward": (c_int, [_P, _P, c_int64, c_float, _P, c_int, _P]),
     "ddpmir_freq_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "ddpmir_ssim_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
+    "ddpmir_huber": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
+    "ddpmir_huber_backward": (c_int, [_P, _P, c_int64, c_float, c_float, _P, c_int, _P]),
+    "ddpmir_color_l1_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P]),
     "ddpmir_sumsq": (c_int, [_P, c_int64, _P, _P]),
     "ddpmir_adamw_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P, c_float, _P]),
 }

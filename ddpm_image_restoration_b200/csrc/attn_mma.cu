@@ -416,9 +416,14 @@ template <int DEG> __device__ __forceinline__ float ex2_poly_bounded(float x) {
 }
 
 // kmax[b, h] = max_j |k_j|  (bf16 values as the MMA sees them)
-template <int HD>
+__device__ __forceinline__ float sumsq_f16x2(uint32_t v) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    return f.x * f.x + f.y * f.y;
+}
+template <int HD, bool F16 = false>
 __global__ void __launch_bounds__(256)
-attn_kbound_kernel(const bf16* __restrict__ qkv, float* __restrict__ kmax, int L, int C) {
+attn_kbound_kernel(const bf16* __restrict__ qkv, float* __restrict__ kmax, int L, int C, int* __restrict__ zero_me = nullptr) {
+    if (zero_me && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_me = 0;   // the f16 tier's decline counter
     const int b = blockIdx.y, h = blockIdx.x;
     const long long rstride = 3LL * C;
     const bf16* kbase = qkv + (long long)b * L * rstride + C + (long long)h * HD;
@@ -430,7 +435,8 @@ attn_kbound_kernel(const bf16* __restrict__ qkv, float* __restrict__ kmax, int L
 #pragma unroll
         for (int c = 0; c < HD / 8; ++c) {
             const uint4 v = __ldg(kp + c);
-            ss += sumsq_bf16x2(v.x) + sumsq_bf16x2(v.y) + sumsq_bf16x2(v.z) + sumsq_bf16x2(v.w);
+            ss += F16 ? sumsq_f16x2(v.x) + sumsq_f16x2(v.y) + sumsq_f16x2(v.z) + sumsq_f16x2(v.w)
+                      : sumsq_bf16x2(v.x) + sumsq_bf16x2(v.y) + sumsq_bf16x2(v.z) + sumsq_bf16x2(v.w);
         }
         best = fmaxf(best, ss);
     }
@@ -636,14 +642,16 @@ int launch_bounded(const void* qkv, void* out, const float* kmax, int* flags, in
 int g_expmode = -1;   // -1 = auto: mode 3 (25 % of the exps on the FMA pipe) at head_dim 8, mode 0 otherwise (measured on B200)
 int g_mt = 1;
 int g_poly = -1;      // bounded kernel: score tiles of 8 on the FMA pipe (-1 = auto), +8 = degree-2 instead of degree-3 polynomial
+int g_split16 = 0;    // half-precision tier (attn_tc16.cu): MUFU share of its two FMA-pipe variants, 0 = default
 
 }  // namespace
 
 // test / tuning hook: expmode 0 = fp32 ex2 + cvt pack, 1 = packed bf16x2 ex2, 2 = fp32 ex2 + truncating pack;
 // +16 selects two 16-row tiles per warp (head_dim 8/16 only); bits 8..: (value + 1) of the bounded kernel's POLY/pack choice
 extern "C" int ddpmir_attention_set_expmode(int mode) {
-    if (mode < 0) { g_expmode = -1; g_mt = 1; g_poly = -1; return DDPMIR_OK; }
-    g_poly = (mode >> 8) - 1;
+    if (mode < 0) { g_expmode = -1; g_mt = 1; g_poly = -1; g_split16 = 0; return DDPMIR_OK; }
+    g_split16 = (mode >> 16) & 0xfff;             // bits 16..23: attn_tc16's split (see ddpmir_attention_tc16)
+    g_poly = ((mode >> 8) & 255) - 1;           // bits 8..15: (value + 1) of the bounded kernels' choice; +32 skips the half-precision tier
     mode &= 255;
     g_expmode = mode & 15;
     if (g_expmode > 4) g_expmode = 0;
@@ -652,7 +660,9 @@ extern "C" int ddpmir_attention_set_expmode(int mode) {
 }
 
 int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float qscale, cudaStream_t st);
-int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, cudaStream_t st);
+int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, int redo, cudaStream_t st);
+int ddpmir_attention_tc16(const void* qkv, void* out, const float* kmax, int* flags, int* declined, int B, int L, int C, int heads, int split,
+                          cudaStream_t st);
 
 static int attention_mma_scaled(const void* qkv, int B, int L, int C, int heads, void* out, float* lse, float scale_log2, const int* redo,
                                 bool force_mt1, cudaStream_t st) {
@@ -725,7 +735,7 @@ extern "C" int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, 
         const bool rn = (sel & 8) != 0;   // +8: degree-2 polynomial
         int rc = DDPMIR_ERR_UNSUPPORTED;
         // long sequences: tcgen05 / TMEM kernel (attn_tc.cu); +64 in the tuning hook keeps the mma.sync kernel
-        if (tc_ok) rc = ddpmir_attention_tc(qkv, out, kmax, flags, B, L, C, heads, sel & 31, st);
+        if (tc_ok) rc = ddpmir_attention_tc(qkv, out, kmax, flags, B, L, C, heads, sel & 31, 0, st);
         if (rc == DDPMIR_ERR_UNSUPPORTED) {
 #define GB(HD) (rn ? (poly == 0 ? launch_bounded<HD, 0, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \
                       poly == 1 ? launch_bounded<HD, 1, 2>(qkv, out, kmax, flags, B, L, C, heads, st) : \
@@ -749,4 +759,61 @@ extern "C" int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, 
     int rc = attention_mma_scaled(qkv, B, L, C, heads, out, nullptr, 1.f, nullptr, false, st);
     if (rc != DDPMIR_ERR_UNSUPPORTED) return rc;
     return ddpmir_attention_simt(qkv, DDPMIR_BF16, B, L, C, heads, out, 0.69314718055994531f, st);
+}
+
+// ---- binary16 qkv: the three-tier path of the full-resolution blocks ----------------------------------------------------
+namespace {
+// dst (bf16) = src (f16), only when the half-precision tier declined at least one CTA
+__global__ void __launch_bounds__(256)
+f16_to_bf16_if_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n8, const int* __restrict__ declined) {
+    if (*declined == 0) return;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+        const uint4 v = __ldg(src + i);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ob[k] = __float22bfloat162_rn(__half22float2(h[k]));
+        dst[i] = o;
+    }
+}
+inline size_t f16_header_bytes(int B, int L, int heads) {
+    const size_t n = (size_t)B * heads + (size_t)B * heads * ceil_div(L, 128) + 4;
+    return (n * 4 + 255) / 256 * 256;
+}
+}  // namespace
+
+extern "C" size_t ddpmir_attention_prescaled_f16_workspace(int B, int L, int C, int heads) {
+    return f16_header_bytes(B, L, heads) + (size_t)B * L * 3 * C * 2;
+}
+
+extern "C" int ddpmir_attention_prescaled_f16(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
+                                              ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(qkv && out && workspace, "attention_prescaled_f16: null pointer");
+    DDPMIR_CHECK_ARG(B > 0 && L > 0 && heads > 0 && C % heads == 0, "attention_prescaled_f16: bad shape");
+    DDPMIR_CHECK_ARG(B <= 65535 && heads <= 65535, "attention_prescaled_f16: grid too large");
+    const int hd = C / heads;
+    if ((hd != 8 && hd != 16) || L < 1024 || L % 128 != 0) {
+        ddpmir_set_error("attention_prescaled_f16: head_dim 8/16 and L >= 1024, L %% 128 == 0 only (got hd %d, L %d)", hd, L);
+        return DDPMIR_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* kmax = (float*)workspace;
+    int* flags = (int*)(kmax + (size_t)B * heads);
+    int* declined = flags + (size_t)B * heads * ceil_div(L, 128);
+    void* copy = (char*)workspace + f16_header_bytes(B, L, heads);
+    if (hd == 8) attn_kbound_kernel<8, true><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C, declined);
+    else attn_kbound_kernel<16, true><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C, declined);
+    DDPMIR_LAUNCH_CHECK();
+    // tier 1: S and P in binary16, logit bound <= 11
+    int rc = ddpmir_attention_tc16(qkv, out, kmax, flags, declined, B, L, C, heads, g_split16, st);
+    if (rc != DDPMIR_OK) return rc;
+    // tiers 2 and 3 read bf16: a copy made only if some CTA was declined (the kernels below return at once otherwise)
+    const long long n8 = (long long)B * L * 3 * C / 8;
+    f16_to_bf16_if_kernel<<<148 * 8, 256, 0, st>>>((const uint4*)qkv, (uint4*)copy, n8, declined);
+    DDPMIR_LAUNCH_CHECK();
+    const int sel = g_poly >= 0 ? (g_poly & 31) : 20;
+    rc = ddpmir_attention_tc(copy, out, kmax, flags, B, L, C, heads, sel, 1, st);           // tier 2: P in bf16, bound <= 60
+    if (rc != DDPMIR_OK) return rc;
+    return attention_mma_scaled(copy, B, L, C, heads, out, nullptr, 1.f, flags, true, st);  // tier 3: exact online-max kernel
 }

@@ -32,7 +32,7 @@ constexpr int CTAS_PER_SM = 2;                  // two CTAs share an SM (and its
 constexpr int TMEM_COLS = 512 / CTAS_PER_SM;
 constexpr int NBUF = 1;                         // S buffers per warpgroup (released as soon as S sits in registers, so one suffices)
 constexpr int LAG = NWG * NBUF;                 // S/P buffers in flight
-constexpr int NSTAGE = 10;                      // K/V ring (a stage is released by the PV of its tile)
+constexpr int NSTAGE = 8;                       // K/V ring (a stage is released by the PV of its tile); a power of two: the stage arithmetic is masks
 // single-role warps after the softmax warps.  One tcgen05.mma costs its issuing warp ~75 cycles of dependent uniform-datapath
 // instructions (measured), so each softmax warpgroup gets its own MMA-issuer warp: it issues PV for a buffer as soon as the
 // warpgroup has written P and, right behind it in the same in-order tensor pipe (no barrier needed), the QK^T that refills
@@ -102,7 +102,9 @@ __device__ __forceinline__ float sumsq_bf16x2(uint32_t v) {
 template <int HD, int POLY, int DEG>
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out, const float* __restrict__ kmax, int* __restrict__ flags,
-               int L, int C) {
+               int L, int C, int redo) {
+    // redo: only the CTAs the half-precision tier (attn_tc16.cu) declined -- flag 1 -- are computed here
+    if (redo && flags[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] == 0) return;
     constexpr int KB = HD / 8;                  // 16-byte blocks per Q / K row that hold data (the MMA always reads 2: K = 16)
     constexpr int NO = HD == 8 ? 16 : 32;       // PV accumulator columns: head_dim | ones | zero padding
     constexpr int STAGE_BLOCKS = 2 + NO / 8;    // K lo, K hi (zeros at head_dim 8) | V blocks, ones block (, zero block)
@@ -121,7 +123,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
     uint64_t* o_full = q_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: the issuers' operands stay in uniform registers
     const int b = blockIdx.z, h = blockIdx.y, row0 = blockIdx.x * TQ;
     const int T = L / TK;
 
@@ -198,18 +201,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
     constexpr uint32_t DESC_HI_V = (uint32_t)(BLK >> 4) | (1u << 14);          // SBO = one block (next 8 output columns)
     if (warp == W_TMA) {
         // ---- TMA producer -------------------------------------------------------------------------------------------
-        if (lane == 0) {
-            int s = 0, ph = 1;
-            for (int j = 0; j < T; ++j) {
-                mbar_wait_parked(&kv_free[s], ph, 2000);
+        const bool leader = elect_one();
+        int s = 0, ph = 1;
+        for (int j = 0; j < T; ++j) {
+            mbar_wait_warp<200>(&kv_free[s], ph);      // plenty of slack (a ring of tiles ahead): sleep between probes
+            if (leader) {
                 unsigned char* st = stages + s * STAGE_BYTES;
                 mbar_expect_tx(&kv_full[s], 2 * KB * BLK);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) tma_load_3d(st + kb * BLK, &tmap, &kv_full[s], C + h * HD + 8 * kb, j * TK, b);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) tma_load_3d(st + (2 + kb) * BLK, &tmap, &kv_full[s], 2 * C + h * HD + 8 * kb, j * TK, b);
-                if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
     } else if (warp >= W_MMA) {
         // ---- MMA issuer of warpgroup g: tiles g, g + NWG, ...; buffer g + NWG * (it & 1) ------------------------------------
@@ -219,11 +224,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         const uint32_t k_lo0 = ((smem_u32(stages) & 0x3FFFF) >> 4) | ((uint32_t)(BLK >> 4) << 16);
         const uint32_t v_lo0 = ((smem_u32(stages + 2 * BLK) & 0x3FFFF) >> 4) | ((uint32_t)(128 >> 4) << 16);   // LBO = next 8 keys
         const int g = warp - W_MMA;
+        const bool leader = elect_one();
         auto qk = [&](int j, int sb) {      // S(j) -> buffer sb
             const int s = j % NSTAGE;
-            mbar_wait_parked(&kv_full[s], (j / NSTAGE) & 1, 500);
+            mbar_wait_warp<0>(&kv_full[s], (j / NSTAGE) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (leader) {
                 umma_bf16(tmem_base + sb * TK, desc_q, ((uint64_t)DESC_HI_K << 32) | (k_lo0 + s * (STAGE_BYTES >> 4)), IDESC_QK, 0u);
                 umma_commit(&s_full[sb]);
             }
@@ -236,12 +242,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
             const int sb = g + NWG * (it % NBUF), s = j % NSTAGE;
             // the warpgroup holds S(j) in registers: refill its buffer with the tile NBUF rounds ahead while it exponentiates
             if (j + NWG * NBUF < T) {
-                mbar_wait_parked(&s_free[sb], (it / NBUF) & 1, 500);
+                mbar_wait_warp<0>(&s_free[sb], (it / NBUF) & 1);
                 qk(j + NWG * NBUF, sb);
             }
-            mbar_wait_parked(&p_full[g], it & 1, 500);
+            mbar_wait_warp<100>(&p_full[g], it & 1);    // P arrives most of a tile later: sleep between probes
             tc_fence_after();
-            if (lane == 0) {
+            if (leader) {
                 const uint32_t v_lo = v_lo0 + s * (STAGE_BYTES >> 4);
 #pragma unroll
                 for (int ks = 0; ks < TK / 16; ++ks)
@@ -274,7 +280,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
         for (int j = g; j < T; j += NWG, ++it) {
             const int sb = g + NWG * (it % NBUF);
             const uint32_t s_addr = lane_base + sb * TK;
-            mbar_wait_parked(&s_full[sb], (it / NBUF) & 1, 500);
+            mbar_wait_warp<0>(&s_full[sb], (it / NBUF) & 1);
             tc_fence_after();
             uint32_t sv[TK / 32][32], pk[TK / 32][16];
 #pragma unroll
@@ -285,7 +291,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
 #pragma unroll
             for (int c = 0; c < TK / 32; ++c) exp_pack(sv[c], pk[c]);
             if (it > 0) {                             // PV of the previous tile has read P
-                mbar_wait_parked(&p_free[g], (it - 1) & 1, 500);
+                mbar_wait_warp<0>(&p_free[g], (it - 1) & 1);
                 tc_fence_after();
             }
 #pragma unroll
@@ -333,22 +339,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out,
 }
 
 template <int HD, int POLY, int DEG>
-int launch(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, cudaStream_t st) {
+int launch(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int redo, cudaStream_t st) {
     constexpr int NO = HD == 8 ? 16 : 32;
-    // the kernel owns all 512 TMEM columns, so exactly one CTA may live on an SM: ask for more than half of the shared memory
+    // a CTA owns 256 of the 512 TMEM columns: ask for more than a third of the shared memory so that no third CTA lands on the SM
     constexpr int need = NSTAGE * (2 + NO / 8) * BLK + 2 * QBLK + (2 * NSTAGE + 2 * LAG + 2 * NWG + 2) * 8 + 16 + 128;
     constexpr int floor_bytes = (227 * 1024) / (CTAS_PER_SM + 1) + 1024;     // no more than CTAS_PER_SM CTAs fit an SM
     constexpr int smem = need > floor_bytes ? need : floor_bytes;
     static_assert(LAG * TK + NWG * (TK / 2) + 32 <= TMEM_COLS, "TMEM budget");
     auto kern = attn_tc_kernel<HD, POLY, DEG>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (int& done = attr_set.cur(); !done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { ddpmir_set_error("attention_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
-        attr_set = true;
+        done = 1;
     }
     dim3 grid(L / TQ, heads, B);
-    kern<<<grid, NTHREADS, smem, st>>>(tm, (bf16*)out, kmax, flags, L, C);
+    kern<<<grid, NTHREADS, smem, st>>>(tm, (bf16*)out, kmax, flags, L, C, redo);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -357,7 +363,8 @@ int launch(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int 
 
 // qkv [B, L, 3C] bf16 with pre-scaled q; kmax [B*heads] from the key-norm pre-pass; flags [B*heads*L/128].
 // sel: bits 0-2 = score pairs of 8 on the FMA pipe, bits 3-4 = how: 0 degree-3 fp32 polynomial, 1 degree 2, 2 packed bf16 pairs.
-int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, cudaStream_t st) {
+// redo != 0: flags holds the half-precision tier's verdicts; only CTAs with flag 1 run (and overwrite it with their own).
+int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, int redo, cudaStream_t st) {
     const int hd = C / heads;
     if ((hd != 8 && hd != 16) || L % TQ != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return DDPMIR_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
@@ -374,12 +381,12 @@ int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flag
         if (r != CUDA_SUCCESS) { ddpmir_set_error("attention_tc: tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
     }
     const int poly = sel & 7, mode = (sel >> 3) & 3;       // mode 0: degree-3 fp32 polynomial, 1: degree 2, 2: packed bf16 pairs
-#define GP(HD, DEG) (poly == 0 ? launch<HD, 0, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                     poly == 1 ? launch<HD, 1, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                     poly == 2 ? launch<HD, 2, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                     poly == 3 ? launch<HD, 3, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                     poly == 4 ? launch<HD, 4, DEG>(tm, out, kmax, flags, B, L, C, heads, st) : \
-                                 launch<HD, 5, DEG>(tm, out, kmax, flags, B, L, C, heads, st))
+#define GP(HD, DEG) (poly == 0 ? launch<HD, 0, DEG>(tm, out, kmax, flags, B, L, C, heads, redo, st) : \
+                     poly == 1 ? launch<HD, 1, DEG>(tm, out, kmax, flags, B, L, C, heads, redo, st) : \
+                     poly == 2 ? launch<HD, 2, DEG>(tm, out, kmax, flags, B, L, C, heads, redo, st) : \
+                     poly == 3 ? launch<HD, 3, DEG>(tm, out, kmax, flags, B, L, C, heads, redo, st) : \
+                     poly == 4 ? launch<HD, 4, DEG>(tm, out, kmax, flags, B, L, C, heads, redo, st) : \
+                                 launch<HD, 5, DEG>(tm, out, kmax, flags, B, L, C, heads, redo, st))
 #define GT(HD) (mode == 2 ? GP(HD, 1) : mode == 1 ? GP(HD, 2) : GP(HD, 3))
     return hd == 8 ? GT(8) : GT(16);
 #undef GT

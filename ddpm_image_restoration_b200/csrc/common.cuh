@@ -74,6 +74,17 @@ template <> struct Vec8<bf16> {
     }
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: remember the opt-in per device, not per process
+// (a process that moves to a second GPU would otherwise launch there without it).  Returns the slot for the current device.
+struct PerDevice {
+    int v[64] = {0};
+    int& cur() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
+
 // ---- activations ----------------------------------------------------------------------------------------
 // exact (erf) GELU, F.gelu default (webp_inference.py:312); SiLU (webp_inference.py:364)
 __device__ __forceinline__ float act_apply(int act, float v) {

@@ -271,11 +271,11 @@ bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 template <int BLOCK_N, int STAGES>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev& ep, const TcParams& p, cudaStream_t st) {
     constexpr int smem = STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (int& done = attr_set.cur(); !done) {
         cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { ddpmir_set_error("igemm_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
-        attr_set = true;
+        done = 1;
     }
     dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(p.N, BLOCK_N));
     igemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, out, ep, p);
@@ -286,8 +286,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev
 template <int TCOLS>
 int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const EpiDev& ep, const StreamParams& sp, int smem,
                   int grid, cudaStream_t st) {
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
+    static PerDevice attr_smem_dev;
+    if (int& attr_smem = attr_smem_dev.cur(); smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(igemm_tc_stream_kernel<TCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { ddpmir_set_error("igemm_tc_stream: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
         attr_smem = smem;

@@ -23,6 +23,7 @@ __device__ __forceinline__ float ld_any(const void* p, int dtype, long long i) {
 }
 __device__ __forceinline__ void st_any(void* p, int dtype, long long i, float v) {
     if (dtype == DDPMIR_F32) reinterpret_cast<float*>(p)[i] = v;
+    else if (dtype == DDPMIR_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
     else reinterpret_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
 }
 
@@ -54,8 +55,11 @@ static inline int check_epi(const ddpmir_epilogue_t* e, int N) {
     if (e->freq_mode == 1 && (N & 1)) { ddpmir_set_error("epilogue: freq_mode 1 needs even N"); return DDPMIR_ERR_INVALID; }
     if (e->freq_mode == 2 && (!e->bias2 || !e->bias)) { ddpmir_set_error("epilogue: freq_mode 2 needs bias and bias2"); return DDPMIR_ERR_INVALID; }
     const int dts[4] = {e->out_dtype, e->out2_dtype, e->mul_dtype, e->res_dtype};
-    for (int i = 0; i < 4; ++i)
-        if (dts[i] != DDPMIR_F32 && dts[i] != DDPMIR_BF16) { ddpmir_set_error("epilogue: bad dtype field %d", dts[i]); return DDPMIR_ERR_INVALID; }
+    for (int i = 0; i < 4; ++i)     // binary16 only as an OUTPUT format (the qkv of the half-precision attention tier)
+        if (dts[i] != DDPMIR_F32 && dts[i] != DDPMIR_BF16 && !(i < 2 && dts[i] == DDPMIR_F16)) {
+            ddpmir_set_error("epilogue: bad dtype field %d", dts[i]);
+            return DDPMIR_ERR_INVALID;
+        }
     return DDPMIR_OK;
 }
 
@@ -131,6 +135,16 @@ __device__ __forceinline__ void st16_any(void* base, int dtype, long long idx, c
         float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
 #pragma unroll
         for (int i = 0; i < 4; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if (dtype == DDPMIR_F16) {
+        uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(base) + idx);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint4 r;
+            __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
+            p[i] = r;
+        }
     } else {
         uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + idx);
 #pragma unroll

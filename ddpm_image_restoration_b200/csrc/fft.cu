@@ -226,7 +226,8 @@ row_fft_affine_kernel(const float* __restrict__ x, float2* __restrict__ ws, long
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int setup_smem() {
-    static bool done = false;
+    static PerDevice done_dev;
+    int& done = done_dev.cur();
     if (done) return DDPMIR_OK;
     const int bytes = 2 * FFT_ELEMS * sizeof(float2);
     cudaError_t e = cudaFuncSetAttribute(row_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -238,7 +239,7 @@ int setup_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(row_ifft_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(row_fft_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { ddpmir_set_error("fft: shared-memory opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
-    done = true;
+    done = 1;
     return DDPMIR_OK;
 }
 

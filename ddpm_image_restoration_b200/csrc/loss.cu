@@ -189,6 +189,55 @@ mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float c
     }
 }
 
+// Huber loss (nn.HuberLoss(reduction='mean', delta), 0409_method.ipynb#c0:L438, 567): 0.5 d^2 if |d| <= delta else delta (|d| - 0.5 delta)
+__global__ void __launch_bounds__(256)
+huber_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float delta, double* __restrict__ acc) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+        const float d[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ad = fabsf(d[k]);
+            s += ad <= delta ? 0.5f * d[k] * d[k] : delta * (ad - 0.5f * delta);
+        }
+    }
+    s = warp_sum(s);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += (double)red[w];
+        atomicAdd(acc, v);
+    }
+}
+__global__ void __launch_bounds__(256)
+huber_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float delta, float coef, float* __restrict__ da, long long n,
+                 int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = a[i] - b[i];
+        const float v = coef * fminf(fmaxf(d, -delta), delta);       // d inside the quadratic zone, +-delta outside
+        da[i] = accumulate ? da[i] + v : v;
+    }
+}
+// colour L1 (0409_method.ipynb#c0:L67-76): d/dpred of 0.25 L1_R + 0.5 L1_G + 0.25 L1_B on x01 = clamp(0.5 x + 0.5, 0, 1), each L1 a
+// mean over B*H*W.  The clamp passes gradient strictly inside (0, 1) (torch.clamp's backward masks with min <= x <= max; on
+// the boundary the difference of two clamped values has measure-zero support, so the convention does not show in practice).
+__global__ void __launch_bounds__(256)
+color_l1_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, int HW, long long n, float coef,
+                    float* __restrict__ dpred, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / HW) % 3);
+        const float p01 = __fadd_rn(__fmul_rn(pred[i], 0.5f), 0.5f), t01 = __fadd_rn(__fmul_rn(target[i], 0.5f), 0.5f);
+        const float a = fminf(fmaxf(p01, 0.f), 1.f), b = fminf(fmaxf(t01, 0.f), 1.f);
+        const float pass = (p01 >= 0.f && p01 <= 1.f) ? 1.f : 0.f;
+        const float sgn = a > b ? 1.f : (a < b ? -1.f : 0.f);
+        const float v = coef * (c == 1 ? 0.5f : 0.25f) * pass * sgn;
+        dpred[i] = accumulate ? dpred[i] + v : v;
+    }
+}
+
 __global__ void scale_kernel(const double* __restrict__ acc, double scale, float* __restrict__ out) { out[0] = (float)(acc[0] * scale); }
 
 }  // namespace
@@ -231,6 +280,41 @@ extern "C" int ddpmir_mse_backward(const float* a, const float* b, int64_t n, fl
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     mse_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (float)(2.0 * weight / (double)n), da, n, accumulate);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+extern "C" int ddpmir_huber(const float* a, const float* b, int64_t n, float delta, float* out_scalar, double* ws, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(a && b && out_scalar && ws && n > 0 && n % 4 == 0 && delta > 0.f, "huber: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(ws, 0, sizeof(double), st);
+    int grid = (int)((n / 4 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    huber_kernel<<<grid, 256, 0, st>>>(a, b, n / 4, delta, ws);
+    scale_kernel<<<1, 1, 0, st>>>(ws, 1.0 / (double)n, out_scalar);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+extern "C" int ddpmir_huber_backward(const float* a, const float* b, int64_t n, float delta, float weight, float* da, int accumulate,
+                                     ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(a && b && da && n > 0 && delta > 0.f, "huber_backward: bad arguments");
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    huber_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, delta, (float)((double)weight / (double)n), da, n, accumulate);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+extern "C" int ddpmir_color_l1_backward(const float* pred, const float* target, int B, int H, int W, float weight, float* dpred,
+                                        int accumulate, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(pred && target && dpred && B > 0 && H > 0 && W > 0, "color_l1_backward: bad arguments");
+    const long long n = (long long)B * 3 * H * W;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    // chain rule of x01 = 0.5 x + 0.5 and the mean over B*H*W per channel
+    color_l1_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, H * W, n, (float)(0.5 * (double)weight / ((double)B * H * W)),
+                                                                  dpred, accumulate);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

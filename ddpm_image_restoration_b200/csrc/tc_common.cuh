@@ -170,3 +170,33 @@ static __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t 
     }
     __trap();
 }
+
+// mbarrier wait, written as ONE asm block so that the compiler sees no divergent loop (no BSSY/BSYNC, no vote): when the phase
+// has already completed -- the usual case for the softmax warps -- it costs three instructions (counter, try_wait, branch).
+// SLEEP_NS > 0: a warp with slack (the issuers waiting for P, the TMA warp waiting for a free stage) sleeps between probes
+// instead of spinning through the softmax warps' issue slots.  A protocol bug must trap, never hang the GPU: the spin is
+// bounded (try_wait itself blocks for a hardware-defined time, so 2^22 probes are seconds).
+template <int SLEEP_NS>
+static __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 q, c, 0x400000;\n\t"
+        "@!q trap;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t"
+        "}"
+        :: "r"(smem_u32(bar)), "r"(parity), "n"(SLEEP_NS > 0 ? SLEEP_NS : 20) : "memory");
+}
+static __device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}

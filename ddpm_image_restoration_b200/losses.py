@@ -1,6 +1,7 @@
-"""Loss functions with the reference's names, as fused CUDA reductions.  FORWARD VALUES ONLY for now: the training
-step (webp_training.py:476-537) needs the backward kernels of every UNet op, which are not built yet, so these return
-plain tensors without autograd history.
+"""Loss functions with the reference's names, as fused CUDA reductions.  These return the loss VALUE as a plain tensor
+(no autograd history: nothing in this package uses autograd); the matching gradient kernels are in ops_train
+(`frequency_aware_loss_backward`, `color_preservation_loss_backward`, `huber_color_loss_backward`) and are what
+training.Trainer calls for the training step (webp_training.py:476-537).
 
   color_loss                conv_deep.ipynb#c0:L60-73        0.25 L1_R + 0.5 L1_G + 0.25 L1_B on clamped [0,1] images
   color_preservation_loss   0409_method.ipynb#c0:L64-82      color_loss + 0.5 (1 - SSIM)
@@ -41,3 +42,24 @@ def frequency_aware_loss(pred, target):
     count = float(B * H * (W // 2 + 1))                             # elements of one channel's rfft2
     freq = (terms[0] + 0.5 * terms[1]).float() / count
     return spatial + 0.5 * freq + 0.3 * (1.0 - ops.ssim(pred, target, clamp01=False))
+
+
+def huber_loss(pred, target, delta=1.0):
+    """nn.HuberLoss(reduction='mean', delta=1.0), the `huber_loss_fn` of 0409_method.ipynb#c0:L438."""
+    pred, target = pred.contiguous().float(), target.contiguous().float()
+    if pred.shape != target.shape:
+        raise ValueError("huber_loss: shapes differ")
+    return ops.huber(pred, target, delta)
+
+
+def color_weight_for_epoch(epoch):
+    """0409_method.ipynb#c0:L573: the colour term's weight grows with the epoch, min(1.0, 0.2 + 0.02 * epoch)."""
+    return min(1.0, 0.2 + epoch * 0.02)
+
+
+def huber_color_loss(pred_noise, noise, xt, x0, epoch=0):
+    """The 0409 notebook's training loss (#c0:L567-574): huber(pred_noise, x0 - xt) + w(epoch) * color_preservation_loss(xt +
+    pred_noise, x0).  Returns (loss, huber, colour) like the loop that logs both terms."""
+    h = huber_loss(pred_noise, noise)
+    col = color_preservation_loss(ops.lincomb(xt.contiguous().float(), 1.0, pred_noise.contiguous().float(), 1.0), x0)
+    return h + color_weight_for_epoch(epoch) * col, h, col

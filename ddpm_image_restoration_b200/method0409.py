@@ -206,7 +206,8 @@ class JPEGDiffusionModel(nn.Module):
         a = ops.groupnorm_apply(h1, st, sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ops.ACT_SILU, out_dtype=dt)
         h2 = ops.conv3x3(a, W["conv2_w"], co, impl, out_dtype=dt, bias=sd[f"{p}.conv2.bias"])
         Bn, H, Wd, _ = h2.shape
-        qkv = ops.gemm(h2, W["in_w"], 3 * co, impl, bias=W["in_b"])
+        qdt = ops.qkv_dtype_for_attention(H * Wd, co // self.HEADS) if dt == torch.bfloat16 else None
+        qkv = ops.gemm(h2, W["in_w"], 3 * co, impl, out_dtype=qdt, bias=W["in_b"])
         if dt == torch.bfloat16:
             ao = ops.attention_prescaled(qkv.view(Bn, H * Wd, 3 * co), self.HEADS).view(Bn, H, Wd, co)
         else:

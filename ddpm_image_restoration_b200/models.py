@@ -152,6 +152,12 @@ class _RestorationUNet(nn.Module):
         self._packed = None
         return super().load_state_dict(*a, **k)
 
+    def invalidate_packed(self):
+        """Drop the pre-packed weight copies.  prepack() notices load_state_dict, .to()/.cuda(), set_precision and in-place
+        edits that bump a parameter's version counter (nn.init.*_, p.copy_(), optimizer steps of torch.optim); writes through
+        `p.data` or raw kernels bypass that counter -- call this after them (training.Trainer does)."""
+        self._packed = None
+
     def _apply(self, fn, *a, **k):
         self._packed = None
         return super()._apply(fn, *a, **k)
@@ -159,7 +165,7 @@ class _RestorationUNet(nn.Module):
     # -- weight pre-packing (once per precision; OIHW fp32 -> [N, (kh,kw,cin)] in the activation dtype) ----------
     def prepack(self):
         dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        key = (self.precision, next(self.parameters()).device)
+        key = (self.precision, next(self.parameters()).device, sum(p._version for p in self.parameters()))
         if self._packed is not None and self._packed_key == key:
             return self._packed
         sd = {k: v.detach() for k, v in self.state_dict().items()}
@@ -233,7 +239,10 @@ class _RestorationUNet(nn.Module):
     # -- forward -------------------------------------------------------------------------------------------
     def forward(self, x, t, compression_level=None):
         if self.training:
-            raise NotImplementedError("the training step (backward kernels) is not part of this build yet; call .eval()")
+            raise NotImplementedError(
+                "forward() is the inference path (no autograd history); call .eval() for inference, or use "
+                "ddpm_image_restoration_b200.training.Trainer(model).train_step(xt, t, x0) for the training step "
+                "(webp_training.py:476-537: explicit forward tape + hand-written backward kernels)")
         if not x.is_cuda:
             raise RuntimeError("the B200 UNet runs on CUDA only (no CPU fallback)")
         with torch.no_grad():
@@ -316,7 +325,8 @@ class _RestorationUNet(nn.Module):
         a = ops.groupnorm_apply(h1, st, sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ops.ACT_GELU, out_dtype=dt)
         h2, h2_op = ops.conv3x3(a, W["conv2_w"], co, impl, out_dtype=f32, out2_dtype=dt, bias=sd[f"{p}.conv2.bias"])
         Bn, H, Wd, _ = h2.shape
-        qkv = ops.gemm(h2_op, W["in_w"], 3 * co, impl, bias=W["in_b"])
+        qdt = ops.qkv_dtype_for_attention(H * Wd, co // fam["heads"]) if dt == torch.bfloat16 else None
+        qkv = ops.gemm(h2_op, W["in_w"], 3 * co, impl, out_dtype=qdt, bias=W["in_b"])
         if dt == torch.bfloat16:
             ao = ops.attention_prescaled(qkv.view(Bn, H * Wd, 3 * co), fam["heads"]).view(Bn, H, Wd, co)
         else:

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, BF16, F32,  # noqa: F401
+from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, BF16, F16, F32,  # noqa: F401
                    IMPL_AUTO, IMPL_SIMT, IMPL_TENSOR, Epilogue)
 
 
@@ -231,6 +231,15 @@ def mse(a, b):
     return out[0]
 
 
+def huber(a, b, delta=1.0):
+    """nn.HuberLoss(reduction='mean', delta)(a, b), 0409_method.ipynb#c0:L438."""
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    ws = torch.empty((1,), dtype=torch.float64, device=a.device)
+    _lib.check(_lib.lib().ddpmir_huber(_p(_f32(a, "a")), _p(_f32(b, "b")), a.numel(), float(delta), _p(out), _p(ws), _stream()), "huber")
+    LAUNCHES[0] += 2
+    return out[0]
+
+
 def ssim(x, y, clamp01=False):
     """SSIM of the [0,1] images x*0.5+0.5, y*0.5+0.5 (pytorch_msssim.ssim semantics), x, y [B,C,H,W] in [-1,1]."""
     B, C, H, W = x.shape
@@ -329,8 +338,9 @@ def _epi(out_dtype, out2=None, bias=None, bias2=None, row_bias=None, img_scale=N
     for t in (bias, bias2, row_bias, img_scale):
         _f32(t, "epilogue vector")
     dt = lambda t: F32 if t is None else _code(t.dtype)
+    oc = lambda d: F16 if d == torch.float16 else _code(d)      # binary16 only as an output format
     return Epilogue(a(bias), a(bias2), a(row_bias), a(img_scale), a(mul), a(res), a(out2), act, freq_mode, bs, low,
-                    _code(out_dtype), dt(out2), dt(mul), dt(res))
+                    oc(out_dtype), F32 if out2 is None else oc(out2.dtype), dt(mul), dt(res))
 
 
 def _igemm(kind, x, w, N, impl, out_dtype, out2_dtype, epi):
@@ -373,12 +383,27 @@ def attention(qkv, heads, impl=IMPL_AUTO):
 Q_PRESCALE_LOG2E = 1.4426950408889634   # attention_prescaled expects q * log2(e) / sqrt(head_dim)
 
 
+def qkv_dtype_for_attention(L, head_dim):
+    """dtype the in_proj GEMM should write for attention_prescaled: binary16 for the long sequences of the full-resolution
+    blocks (three-tier tcgen05 path, ddpmir_attention_prescaled_f16), bf16 otherwise."""
+    return torch.float16 if head_dim in (8, 16) and L >= 1024 and L % 128 == 0 else torch.bfloat16
+
+
 def attention_prescaled(qkv, heads):
-    """bf16 qkv [B, L, 3C] whose q third already carries log2(e)/sqrt(head_dim) -> [B, L, C]."""
+    """qkv [B, L, 3C] whose q third already carries log2(e)/sqrt(head_dim) -> bf16 [B, L, C].  bf16 qkv: bounded / exact
+    kernels of any shape; binary16 qkv (see qkv_dtype_for_attention): the three-tier path for head_dim 8/16, L >= 1024."""
     B, L, C3 = qkv.shape
     C = C3 // 3
+    if qkv.dtype == torch.float16:
+        out = torch.empty((B, L, C), dtype=torch.bfloat16, device=qkv.device)
+        nbytes = _lib.lib().ddpmir_attention_prescaled_f16_workspace(B, L, C, heads)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
+        with _timed("attention", (B, L, C, heads), 5):   # key norms, f16 tier, conditional bf16 copy, bf16 tier, exact redo
+            _lib.check(_lib.lib().ddpmir_attention_prescaled_f16(_p(qkv), B, L, C, heads, _p(ws), _p(out), _stream()),
+                       "attention_prescaled_f16")
+        return out
     if qkv.dtype != torch.bfloat16:
-        raise TypeError("attention_prescaled is the bf16 inference path")
+        raise TypeError("attention_prescaled is the bf16 / binary16 inference path")
     out = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)
     nbytes = _lib.lib().ddpmir_attention_prescaled_workspace(B, L, heads)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)

@@ -187,6 +187,43 @@ def frequency_aware_loss_backward(pred, target, upstream=1.0):
     return dpred
 
 
+def color_preservation_loss_backward(pred, target, upstream=1.0, include_ssim=True, out=None):
+    """d color_preservation_loss(pred, target) / d pred (0409_method.ipynb#c0:L64-82: colour L1 + 0.5 (1 - SSIM) on images
+    clamped to [0,1]), scaled by `upstream`; accumulated into `out` when given."""
+    B, C, H, W = pred.shape
+    if C != 3:
+        raise _lib.DdpmirError("color_preservation_loss needs 3-channel images")
+    lib = _lib.lib()
+    dpred = out if out is not None else torch.empty_like(pred)
+    _lib.check(lib.ddpmir_color_l1_backward(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B, H, W, float(upstream), _p(dpred),
+                                            int(out is not None), _stream()), "color_l1_backward")
+    LAUNCHES[0] += 1
+    if include_ssim:
+        ws = torch.empty((B * C * 3 * (H - 10) * (W - 10),), dtype=F32, device=pred.device)
+        _lib.check(lib.ddpmir_ssim_backward(_p(pred), _p(target), B * C, H, W, 1, -0.5 * upstream, _p(dpred), _p(ws), _stream()),
+                   "ssim_backward")
+        LAUNCHES[0] += 2
+    return dpred
+
+
+def huber_backward(a, b, delta=1.0, upstream=1.0, out=None):
+    """d HuberLoss(mean, delta)(a, b) / d a, scaled by `upstream`; accumulated into `out` when given."""
+    da = out if out is not None else torch.empty_like(a)
+    _lib.check(_lib.lib().ddpmir_huber_backward(_p(_f32(a, "a")), _p(_f32(b, "b")), a.numel(), float(delta), float(upstream), _p(da),
+                                                int(out is not None), _stream()), "huber_backward")
+    LAUNCHES[0] += 1
+    return da
+
+
+def huber_color_loss_backward(pred_noise, noise, xt, x0, color_weight, delta=1.0):
+    """Gradient wrt pred_noise of the 0409 notebook's training loss (#c0:L567-574):
+    huber(pred_noise, noise) + color_weight * color_preservation_loss(xt + pred_noise, x0)."""
+    from .ops import lincomb
+    d = huber_backward(pred_noise, noise, delta)
+    recon = lincomb(xt, 1.0, pred_noise, 1.0)
+    return color_preservation_loss_backward(recon, x0, upstream=color_weight, out=d)
+
+
 def sumsq(x, acc):
     _lib.check(_lib.lib().ddpmir_sumsq(_p(_f32(x, "x")), x.numel(), _p(acc), _stream()), "sumsq")
     LAUNCHES[0] += 1

@@ -17,6 +17,7 @@ import torch
 
 from . import ops
 from . import ops_train as T
+from . import parallel
 from .models import _BLOCKS, _FAMILY, _groups
 
 F32 = torch.float32
@@ -36,7 +37,7 @@ def grad_span_starts(model):
 
 class Trainer:
     def __init__(self, model, lr=2e-4, weight_decay=1e-5, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=1.0, dropout=0.1,
-                 seed=0, overlap_allreduce=True, bucket_bytes=64 << 20):
+                 seed=0, overlap_allreduce=True, bucket_bytes=64 << 20, scheduler="cosine_warm_restarts"):
         if model.family not in ("webp", "jpeg"):
             raise NotImplementedError("training kernels cover the WebP/JPEG families (DCT frequency block) only")
         self.model = model
@@ -58,9 +59,15 @@ class Trainer:
         self._norm_acc = torch.zeros((1,), dtype=torch.float64, device=dev)
         # gradient buckets for the data-parallel all-reduce: the backward finishes the blocks in reverse registration order,
         # so every finished block closes a contiguous tail [start(block), previous start) of the flat buffer
-        self.overlap_allreduce, self.bucket_bytes = overlap_allreduce, bucket_bytes
+        self.overlap_allreduce = overlap_allreduce
         self._span_start = grad_span_starts(model)
-        self._ar_pending, self._ar_hi = [], n
+        self.buckets = parallel.GradBuckets(self.flat_grad, bucket_bytes)
+        self._overlap_now = False
+        # per-epoch lr schedule of the reference (webp_training.py:776): CosineAnnealingWarmRestarts(T_0=100, T_mult=2);
+        # `scheduler` may also be None (constant lr) or any object with step() -> lr
+        self.scheduler = parallel.CosineWarmRestarts(lr) if scheduler == "cosine_warm_restarts" else scheduler
+        import torch.distributed as dist
+        self.rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
 
     # ------------------------------------------------------------------------------------------------------------
     def _pack(self):
@@ -102,8 +109,16 @@ class Trainer:
         return ops.cast_bf16(x) if dt == torch.bfloat16 else x
 
     # ------------------------------------------------------------------------------------------------------------
-    def forward_backward(self, xt, t, x0, dropout_seed=None):
-        """One forward + backward of  frequency_aware_loss(xt + model(xt, t, t), x0).  Fills self.grads; returns loss."""
+    def scheduler_step(self):
+        """End of an epoch: advance the lr schedule (webp_training.py:530) and return the new lr."""
+        if self.scheduler is not None:
+            self.lr = float(self.scheduler.step())
+        return self.lr
+
+    def forward_backward(self, xt, t, x0, dropout_seed=None, overlap=False):
+        """One forward + backward of  frequency_aware_loss(xt + model(xt, t, t), x0).  Fills self.grads; returns loss.
+        overlap=True (what train_step passes) lets the backward launch the bucketed gradient all-reduces itself; the caller
+        then MUST call allreduce_grads() before touching the gradients.  Standalone calls leave the gradients local."""
         m = self.model
         fam = _FAMILY[m.family]
         sd = dict(m.named_parameters()); sd.update(dict(m.named_buffers()))
@@ -111,12 +126,14 @@ class Trainer:
         P, dt = self._pack()
         impl = m.impl
         G = self.grads
+        self.buckets.reset()          # raises if a previous overlapped backward was never finished
+        self._overlap_now = bool(overlap and self.overlap_allreduce)
         self.flat_grad.zero_()
-        self._ar_pending, self._ar_hi = [], self.flat_grad.numel()
         xt = xt.contiguous().float(); x0 = x0.contiguous().float(); t = t.contiguous().float()
         B = xt.shape[0]
         p_drop = self.dropout_p
-        dseed = (self.seed * 1000003 + self.step_count) if dropout_seed is None else dropout_seed
+        # every rank draws its own dropout masks (the ranks hold different images)
+        dseed = ((self.seed * 1000003 + self.step_count) * 4099 + self.rank) if dropout_seed is None else dropout_seed
         with torch.no_grad():
             # ---------------- forward ----------------
             # TimeEmbedding with the pre-activation kept: features -> Linear -> SiLU -> Linear
@@ -323,29 +340,17 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------------------------
     def _grads_final_from(self, lo):
-        """Called by the backward when every gradient at offsets >= lo is final.  With several ranks the finished tail is
-        all-reduced right away in buckets of >= bucket_bytes (NCCL runs them on its own stream, ordered after the kernels
-        enqueued so far), so the collective overlaps the rest of the backward."""
-        import torch.distributed as dist
-        if not (self.overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return
-        if (self._ar_hi - lo) * 4 >= self.bucket_bytes:
-            self._ar_pending.append(dist.all_reduce(self.flat_grad[lo:self._ar_hi], op=dist.ReduceOp.SUM, async_op=True))
-            self._ar_hi = lo
+        """Called by the backward when every gradient at offsets >= lo is final.  In an overlapped step with several ranks
+        the finished tail is all-reduced right away in buckets (parallel.GradBuckets), under the rest of the backward
+        (SURVEY section 8e)."""
+        if self._overlap_now:
+            self.buckets.final_from(lo)
 
     def allreduce_grads(self):
         """Data-parallel gradient averaging over NCCL: whatever the backward has not already sent in buckets goes out as
         one more all-reduce of the head of the flat buffer; then one scale by 1 / world."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        if self._ar_hi > 0:
-            self._ar_pending.append(dist.all_reduce(self.flat_grad[:self._ar_hi], op=dist.ReduceOp.SUM, async_op=True))
-            self._ar_hi = 0
-        for h in self._ar_pending:
-            h.wait()
-        self._ar_pending = []
-        self.flat_grad.mul_(1.0 / dist.get_world_size())
+        self.buckets.finish()
+        self._overlap_now = False
 
     def optimizer_step(self):
         """clip_grad_norm_(max_grad_norm) + AdamW, webp_training.py:522-524."""
@@ -359,7 +364,7 @@ class Trainer:
         self.model._packed = None      # inference weight packs are stale now
 
     def train_step(self, xt, t, x0, dropout_seed=None):
-        loss = self.forward_backward(xt, t, x0, dropout_seed)
+        loss = self.forward_backward(xt, t, x0, dropout_seed, overlap=True)
         self.allreduce_grads()
         self.optimizer_step()
         return loss
@@ -375,4 +380,5 @@ def train_epoch_ddrm_webp(trainer, batches, quality_for_t=None):
     for x0, xt, t in batches:
         loss = trainer.train_step(xt, t.float() / 100.0, x0)
         total += float(loss); n += 1
+    trainer.scheduler_step()          # scheduler.step() once per epoch, webp_training.py:530
     return total / max(n, 1)

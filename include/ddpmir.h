@@ -35,6 +35,7 @@ extern "C" {
 
 #define DDPMIR_F32 0
 #define DDPMIR_BF16 1
+#define DDPMIR_F16 2 /* binary16: only as a GEMM epilogue OUTPUT format and as the qkv of ddpmir_attention_prescaled_f16 */
 
 #define DDPMIR_ACT_NONE 0
 #define DDPMIR_ACT_RELU 1
@@ -232,6 +233,17 @@ size_t ddpmir_attention_prescaled_workspace(int B, int L, int heads);
 int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
                                ddpmir_stream_t stream);
 
+/* The same op for the long sequences of the full-resolution blocks (webp_inference.py:295, 317-321 at H*W >= 1024;
+ * head_dim 8 or 16, L % 128 == 0): qkv is BINARY16 (the in_proj GEMM writes it with epilogue out_dtype DDPMIR_F16, q rows
+ * pre-scaled as above), out is bf16.  Three tiers per 128-row tile, chosen on the device from the tile's Cauchy-Schwarz
+ * logit bound: <= 11 (exp2 domain) scores and probabilities stay in binary16 on the tensor cores (attn_tc16.cu); <= 60
+ * bf16 probabilities (attn_tc.cu); beyond that the exact online-maximum kernel.  workspace:
+ * ddpmir_attention_prescaled_f16_workspace(B, L, C, heads) bytes (flags + room for a bf16 copy of qkv that is written
+ * only when a tile leaves the first tier). */
+size_t ddpmir_attention_prescaled_f16_workspace(int B, int L, int C, int heads);
+int ddpmir_attention_prescaled_f16(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
+                                   ddpmir_stream_t stream);
+
 /* out = x + y * s[b, c] on fp32 NHWC tensors ([B, HW, C]); FrequencyAwareBlock.forward of the 0409 UNet
  * (experiments/code/0409_method.ipynb#c0:L256-263: x + x_freq * attn, attn a per-image per-channel gate).  out2 (optional)
  * receives a copy in out2_dtype for the GEMMs that read the result.  C % 8 == 0. */
@@ -362,6 +374,17 @@ int ddpmir_freq_loss_backward(const float* pred, const float* target, int planes
                               float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream);
 int ddpmir_ssim_backward(const float* x, const float* y, int planes, int H, int W, int clamp01, float weight, float* dx, float* ws,
                          ddpmir_stream_t stream);
+
+/* nn.HuberLoss(reduction='mean', delta) (0409_method.ipynb#c0:L438, 567) over n elements, and its gradient
+ * da (+)= weight * d huber / da.  n % 4 == 0 for the forward; ws: one double. */
+int ddpmir_huber(const float* a, const float* b, int64_t n, float delta, float* out_scalar, double* ws, ddpmir_stream_t stream);
+int ddpmir_huber_backward(const float* a, const float* b, int64_t n, float delta, float weight, float* da, int accumulate,
+                          ddpmir_stream_t stream);
+
+/* Gradient of the colour term of color_preservation_loss (0409_method.ipynb#c0:L67-76; forward: ddpmir_color_l1):
+ * dpred (+)= weight * d(0.25 L1_R + 0.5 L1_G + 0.25 L1_B)/dpred on NCHW fp32 [-1,1] images clamped to [0,1]. */
+int ddpmir_color_l1_backward(const float* pred, const float* target, int B, int H, int W, float weight, float* dpred,
+                             int accumulate, ddpmir_stream_t stream);
 
 /* Optimiser (webp_training.py:521-524, 775): acc += sum x^2 (global gradient norm), and the fused
  * clip_grad_norm_(max_norm) + AdamW update of one tensor (grad_sumsq NULL = no clipping; step >= 1). */

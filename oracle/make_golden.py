@@ -181,11 +181,41 @@ def dct_goldens():
     save("dct_jpeg.npz", x=x, q10=P.jpeg_compress(x, quality=10), q50=P.jpeg_compress(x, quality=50), q90=P.jpeg_compress(x, quality=90))
 
 
-def trajectory256(n_images=1):
-    fam, q, steps = "webp", 10, 80
+def unet256():
+    """unet_{webp,avif,jpeg}_256.npz: one UNet forward at the resolution the bench is quoted on (B=1, L = 65 536 tokens
+    at full resolution), restated oracle (the verbatim reference needs 68.7 GB for one score tensor at this size)."""
+    for fam in ("avif", "webp", "jpeg"):
+        sd = W.make_state_dict(fam, 0)
+        g = torch.Generator().manual_seed(256 + len(fam))
+        clean = W.synthetic_images(1, 256, 256, seed=77)
+        x = clean + 0.1 * torch.randn(clean.shape, generator=g)      # image-like x_t, as the sampler feeds it
+        t = torch.tensor([0.44])
+        t0 = time.time()
+        with torch.no_grad():
+            out = R.unet_forward(sd, x, t, None, fam)
+        save(f"unet_{fam}_256.npz", x=x, t=t, out=out, cpu_seconds=time.time() - t0)
+
+
+def gmm256():
+    """gmm_jpeg_256.npz: GaussianMixtureSampler (0409) at 256x256, 6 steps (i = 5, 4 take the SVD guide at rank 213 / 170,
+    i = 5 the phase consistency), JPEG UNet, restated oracle."""
+    sd = W.make_state_dict("jpeg", 0)
+    clean = W.synthetic_images(1, 256, 256, seed=1234)
+    y = R.codec_roundtrip(clean, 10, "jpeg")
+    steps = 6
+    t0 = time.time()
+    trace = []
+    with torch.no_grad():
+        out = R.gmm_sample(lambda x, t, l: R.unet_forward(sd, x, t, l, "jpeg"), y, steps, philox_noise, coin, trace=trace)
+    save("gmm_jpeg_256.npz", clean_u8=R.quantize_u8(clean), y=y, steps=steps, out=out, x_after_first=trace[0],
+         psnr_out=R.psnr(out, clean), cpu_seconds=time.time() - t0)
+
+
+def trajectory256(n_images=1, fam="webp"):
+    q, steps = {"webp": (10, 80), "avif": (20, 75), "jpeg": (10, 80)}[fam]   # BASELINE configs[0], [1], [2]'s codec/quality
     sd = W.make_state_dict(fam, 0)
     clean = W.synthetic_images(n_images, 256, 256, seed=1234)
-    y = R.codec_roundtrip(clean, q, "webp")
+    y = R.codec_roundtrip(clean, q, fam)
     t0 = time.time()
     trace = []
     def model_fn(x, t, lvl):
@@ -193,7 +223,7 @@ def trajectory256(n_images=1):
         print(f"  step done {time.time() - t0:.0f}s", flush=True)
         return o
     out = R.ddrm_sample(model_fn, y, q, steps, fam, noise_fn=philox_noise, trace=trace)
-    name = "traj256_webp.npz" if n_images == 1 else f"traj256x{n_images}_webp.npz"
+    name = f"traj256_{fam}.npz" if n_images == 1 else f"traj256x{n_images}_{fam}.npz"
     save(name, clean_u8=R.quantize_u8(clean), y_u8=R.quantize_u8(y), quality=q, steps=steps,
          out=out.half(), psnr_in=R.psnr(y, clean), psnr_out=R.psnr(out, clean),
          psnr_each=np.array([R.psnr(out[i:i + 1], clean[i:i + 1]) for i in range(n_images)]),
@@ -206,11 +236,21 @@ if __name__ == "__main__":
     ap.add_argument("--trajectory256", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--images", type=int, default=1)
+    ap.add_argument("--family", default="webp")
+    ap.add_argument("--unet256", action="store_true")
+    ap.add_argument("--gmm256", action="store_true")
+    ap.add_argument("--threads", type=int, default=0)
     args = ap.parse_args()
+    if args.threads:
+        torch.set_num_threads(args.threads)
     if not rl.available():
         sys.exit("reference tree not mounted; goldens can only be minted in the build container")
     if args.trajectory256:
-        trajectory256(args.images)
+        trajectory256(args.images, args.family)
+    elif args.unet256:
+        unet256()
+    elif args.gmm256:
+        gmm256()
     else:
         for fn in (op_goldens, unet_goldens, sampler_goldens, dct_goldens, m0409_goldens):
             if not args.only or args.only in fn.__name__:

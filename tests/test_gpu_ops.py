@@ -336,16 +336,17 @@ def test_attention_tensor_core_bf16(ops, expmode, hd, heads, L):
     assert rel(out2, _attn_ref(qkv, heads)) < 4e-3
 
 
-def _prescaled(qkv, heads, gain=1.0):
-    """bf16 qkv whose q third carries log2(e)/sqrt(hd) (as the packed in_proj produces it) + the fp32 tensor it stands for."""
+def _prescaled(qkv, heads, gain=1.0, dtype=torch.bfloat16):
+    """bf16 (or binary16) qkv whose q third carries log2(e)/sqrt(hd) (as the packed in_proj produces it) + the fp32 tensor it
+    stands for."""
     C = qkv.shape[-1] // 3
     c = 1.4426950408889634 / math.sqrt(C // heads)
     pre = qkv.clone()
     pre[..., :C] *= c * gain
-    pre = bf16_round(pre)
+    pre = pre.to(dtype).float()
     ref = pre.clone()
     ref[..., :C] /= c
-    return pre.to(torch.bfloat16), ref
+    return pre.to(dtype), ref
 
 
 @pytest.mark.parametrize("sel", [-1, 0, 1, 2, 3, 4, 5, 8, 11, 12, 18, 19, 20, 21, 66, 75])
@@ -409,6 +410,87 @@ def test_attention_full_resolution_kernels_agree(ops, hd, heads):
     out_exact = ops.attention(ref.to(torch.bfloat16).cuda(), heads, ops.IMPL_TENSOR).float()
     assert rel(out_tc.cpu(), out_exact.cpu()) < 6e-3
     assert rel(out_mma.cpu(), out_exact.cpu()) < 6e-3
+
+
+def _attn_rows_fp64(ref, heads, rows):
+    """softmax(q k^T / sqrt(hd)) v in float64 on the CPU for the sampled query rows of image 0: [len(rows), C]."""
+    C = ref.shape[-1] // 3
+    hd = C // heads
+    q, k, v = (ref[0, :, i * C:(i + 1) * C].double().view(-1, heads, hd) for i in range(3))
+    out = torch.empty(len(rows), heads, hd, dtype=torch.float64)
+    for h in range(heads):
+        s = (q[rows, h] @ k[:, h].T) / math.sqrt(hd)
+        out[:, h] = torch.softmax(s, dim=-1) @ v[:, h]
+    return out.view(len(rows), C)
+
+
+@pytest.mark.parametrize("split", [0, 2, 4, 5, 7, 3 << 3, 5 << 3])
+@pytest.mark.parametrize("scale", [0.3, 0.8])
+@pytest.mark.parametrize("hd,heads,L", [(8, 8, 2048), (16, 4, 1024), (8, 4, 1152)])
+def test_attention_half_precision_tier(ops, hd, heads, L, scale, split):
+    """attn_tc16.cu (S and P in binary16): scale 0.3 -> logit bound < 2, the degree-4 polynomial variant; 0.8 -> bound < 11, the
+    range-reduced variant; every MUFU / FMA-pipe split, against the fp32 SDPA reference.  The tolerance is tighter than the
+    bf16 tier's: P keeps 11 significand bits."""
+    from ddpm_image_restoration_b200 import _lib
+    C = hd * heads
+    pre, ref = _prescaled(torch.randn(2, L, 3 * C, generator=g(hd + L)) * scale, heads, dtype=torch.float16)
+    assert pre.dtype == ops.qkv_dtype_for_attention(L, hd)
+    _lib.lib().ddpmir_attention_set_expmode(split << 16)
+    try:
+        out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    finally:
+        _lib.lib().ddpmir_attention_set_expmode(-1)
+    want = _attn_ref(ref, heads)
+    assert rel(out, want) < 4e-3
+    # the bf16 entry point (bf16 tier) on the same values
+    out2 = ops.attention_prescaled(pre.to(torch.bfloat16).cuda(), heads).float().cpu()
+    assert rel(out2, want) < 8e-3
+
+
+def test_attention_tiers_mixed_in_one_launch(ops):
+    """CTAs of one launch land in different tiers: most in the half-precision tier, one CTA with logits beyond +-11 in the
+    bf16 tier, one beyond +-60 in the exact kernel."""
+    hd, heads, L = 8, 8, 2048
+    C = hd * heads
+    qkv = torch.randn(2, L, 3 * C, generator=g(91)) * 0.4
+    qkv[0, 256:300, :C] *= 12.0       # CTA 2 of image 0: bound ~ 25 -> bf16 tier
+    qkv[1, 1300:1330, :C] *= 80.0     # CTA 10 of image 1: bound > 60 -> exact kernel
+    pre, ref = _prescaled(qkv, heads, dtype=torch.float16)
+    out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    want = _attn_ref(ref, heads)
+    # tiles that leave the first tier are recomputed from a bf16 copy of qkv: their reference sees the same rounding
+    c = 1.4426950408889634 / math.sqrt(hd)
+    ref_bf = pre.to(torch.bfloat16).float()
+    ref_bf[..., :C] /= c
+    want_bf = _attn_ref(ref_bf, heads)
+    assert torch.isfinite(out).all()
+    keep = torch.ones(2, L, dtype=torch.bool)
+    keep[0, 256:384] = False
+    keep[1, 1280:1408] = False
+    assert rel(out[keep], want[keep]) < 4e-3
+    assert rel(out[0, 256:384], want_bf[0, 256:384]) < 6e-3
+    assert rel(out[1, 1280:1408], want_bf[1, 1280:1408]) < 1e-2
+
+
+@pytest.mark.parametrize("scale", [0.35, 0.8, 1.2])     # logit bound ~2 (a fresh UNet) / ~9 / ~20: the three bounded tiers
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("hd,heads", [(8, 8), (16, 4)])
+def test_attention_full_resolution_vs_fp64_rows(ops, hd, heads, dtype, scale):
+    """L = 65 536 (the bench's full-resolution blocks, head_dim 8 = AVIF, 16 = WebP/JPEG): 384 sampled query rows of the
+    production kernels (binary16 qkv = what the UNet feeds at this length: three-tier path; bf16 qkv: bf16 tier) against a
+    float64 softmax computed on the CPU -- an independent reference, not a sibling kernel."""
+    C, L = hd * heads, 65536
+    qkv = torch.randn(1, L, 3 * C, generator=g(11 + hd)) * scale
+    qkv[0, :, 2 * C:] += 0.3                                   # V with a mean, as feature maps have
+    pre, ref = _prescaled(qkv, heads, dtype=dtype)
+    out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    rows = torch.randperm(L, generator=g(5))[:384]
+    rows[:4] = torch.tensor([0, 127, 128, L - 1])
+    want = _attn_rows_fp64(ref, heads, rows)
+    r = rel(out[0, rows], want)
+    print(f"attention L=65536 hd={hd} {dtype} scale={scale}: rel-L2 of 384 rows vs fp64 softmax = {r:.3e}")
+    assert r < 6e-3
+    assert (out[0, rows].double() - want).abs().max() < 0.02 * want.abs().max() + 1e-3
 
 
 def test_cpu_tensor_raises(ops):

@@ -107,6 +107,24 @@ def test_gmm_sampler_vs_reference_golden(golden):
         assert abs(R.psnr(out, clean) - float(d["psnr_out"])) < 0.05
 
 
+def test_gmm_sampler_256_vs_oracle(golden):
+    """BASELINE config 3's shape (JPEG q=10, 256x256, SVD guide of rank 213 / 170 on 256x256 planes + phase consistency):
+    six GaussianMixtureSampler steps against the restated oracle (oracle/make_golden.py --gmm256)."""
+    import ddpm_image_restoration_b200 as P
+    d = golden("gmm_jpeg_256.npz")
+    y = torch.from_numpy(d["y"])
+    clean = torch.from_numpy(d["clean_u8"]).float() / 255 * 2 - 1
+    m = load_model("jpeg")
+    for precision, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        m.set_precision(precision)
+        s = P.GaussianMixtureSampler(m, num_timesteps=100, noise_fn=philox_noise, coin_fn=coin)
+        out = s.sample(y.cuda(), steps=int(d["steps"])).cpu()
+        r = rel(out, torch.from_numpy(d["out"]))
+        print(f"gmm 256x256 {precision}: rel-L2 vs oracle = {r:.3e}; PSNR {R.psnr(out, clean):.4f} vs {float(d['psnr_out']):.4f} dB")
+        assert r < tol, precision
+        assert abs(R.psnr(out, clean) - float(d["psnr_out"])) < 0.05
+
+
 def test_codec_functions_on_gpu(golden):
     import ddpm_image_restoration_b200 as P
     d = golden("ops.npz")
@@ -134,6 +152,29 @@ def test_trajectory256_webp_psnr(golden, precision, fixture):
     print(f"traj256 {precision} ({y.shape[0]} images): PSNR {got:.4f} dB vs oracle {float(d['psnr_out']):.4f} dB; "
           f"vs oracle images {R.psnr(out, torch.from_numpy(d['out']).float()):.2f} dB")
     assert abs(got - float(d["psnr_out"])) < 0.05
+
+
+@pytest.mark.parametrize("fam,fixture", [("avif", "traj256x2_avif.npz"), ("jpeg", "traj256x2_jpeg.npz")])
+def test_trajectory256_avif_jpeg_psnr(golden, fam, fixture):
+    """The bench configuration itself (BASELINE config 2: AVIF q=20, 256x256, 75 timesteps, head_dim-8 attention over
+    65 536 tokens, bf16 operands) and the JPEG q=10 80-step trajectory (device codec): PSNR of the restored images within
+    0.05 dB of the oracle trajectories (two images each, oracle/make_golden.py --trajectory256 --family ... --images 2)."""
+    import os
+    import ddpm_image_restoration_b200 as P
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, fixture)):
+        pytest.skip(f"{fixture} not minted")
+    d = golden(fixture)
+    clean = torch.from_numpy(d["clean_u8"]).float() / 255 * 2 - 1
+    y = (torch.from_numpy(d["y_u8"]).float() / 255).sub(0.5).mul(2.0)
+    cls = {"avif": P.DDRMAVIFSampler, "jpeg": P.DDRMJPEGSampler}[fam]
+    for precision in ("fp32", "bf16"):
+        m = load_model(fam).set_precision(precision)
+        out = cls(m, seed=NOISE_SEED).sample(y.cuda(), int(d["quality"]), steps=int(d["steps"])).cpu()
+        got = R.psnr(out, clean)
+        print(f"traj256 {fam} {precision} ({y.shape[0]} images): PSNR {got:.4f} dB vs oracle {float(d['psnr_out']):.4f} dB; "
+              f"vs oracle images {R.psnr(out, torch.from_numpy(d['out']).float()):.2f} dB")
+        assert abs(got - float(d["psnr_out"])) < 0.05, precision
 
 
 @pytest.mark.parametrize("q", [10, 50, 90])

@@ -100,14 +100,52 @@ def test_shard_range():
     assert codec_threads_per_rank(16, 8) == 2 and codec_threads_per_rank(4, 8) == 1
 
 
+def test_cosine_warm_restarts_matches_torch():
+    """parallel.CosineWarmRestarts (what Trainer.scheduler_step drives) against the scheduler the reference constructs
+    (webp_training.py:776: CosineAnnealingWarmRestarts(optimizer, T_0=100, T_mult=2)), over three restarts; and a short cycle."""
+    from ddpm_image_restoration_b200.parallel import CosineWarmRestarts
+    for base, T0, Tm, epochs in ((2e-4, 100, 2, 750), (1.5e-4, 3, 2, 40), (1e-3, 5, 1, 23)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=base)
+        ref = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=T0, T_mult=Tm)
+        mine = CosineWarmRestarts(base, T0, Tm)
+        assert mine.lr() == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12)
+        for _ in range(epochs):
+            opt.step(); ref.step()
+            assert mine.step() == pytest.approx(opt.param_groups[0]["lr"], rel=1e-9, abs=1e-18)
+    st = mine.state_dict()
+    other = CosineWarmRestarts(9.0); other.load_state_dict(st)
+    assert other.step() == mine.step()
+
+
 def _rank_main(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
-    from ddpm_image_restoration_b200.parallel import allreduce_mean_, max_over_ranks, shard_range, sum_over_ranks
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ddpm_image_restoration_b200.parallel import (GradBuckets, allreduce_mean_, init_process_group_from_env, max_over_ranks,
+                                                      shard_range, sum_over_ranks)
+    assert init_process_group_from_env() == (rank, world, 0) and dist.get_backend() == "gloo"
     flat = torch.full((1000,), float(rank + 1))      # the training step's flat gradient buffer
     allreduce_mean_(flat)
     assert torch.allclose(flat, torch.full((1000,), 1.5))
+    # the Trainer's bucketed, overlapped gradient all-reduce (GradBuckets): tails of the flat buffer become final in the
+    # order the backward finishes the blocks; the result must equal ONE all-reduce of the whole buffer, bit for bit
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.randn(10007, generator=g)
+    single = grad.clone()
+    allreduce_mean_(single)
+    bk = GradBuckets(grad, bucket_bytes=4 * 1500)
+    for lo in (9000, 8800, 7000, 6999, 3000, 100):       # block starts, descending
+        bk.final_from(lo)
+    assert bk.pending, "some buckets must already be in flight before finish()"
+    try:
+        bk.reset()
+        raise AssertionError("reset() must refuse to drop pending all-reduces")
+    except RuntimeError:
+        pass
+    bk.finish()
+    assert bk.collectives == 4 and not bk.pending and bk.hi == 0      # [7000,10007) [3000,7000) [100,3000) + the head [0,100)
+    assert torch.equal(grad, single)
+    bk.reset()
     lo, hi = shard_range(10, rank, world)
     dist.barrier()
     t = max_over_ranks(1.0 + rank)            # the slowest rank defines the step time
