@@ -12,6 +12,7 @@ Unlike the reference's avif_compress there is no silent JPEG fallback: an AVIF f
 import concurrent.futures as cf
 import io
 import os
+import time
 
 import numpy as np
 import torch
@@ -20,6 +21,8 @@ from . import ops
 
 _POOL = None
 _POOL_THREADS = None
+_AVIF_KW = None           # extra save() arguments of the AVIF encoder, decided once per process (see _avif_save_kwargs)
+CPU_SECONDS = [0.0]       # wall time spent inside _roundtrip_one, summed over the pool's threads (bench.py: codec_cpu_ms_per_step)
 
 
 def host_threads():
@@ -57,15 +60,37 @@ def _clamp_quality(codec, quality):
     return max(0, min(100, q)) if codec == "webp" else max(1, min(100, q))
 
 
+def _avif_save_kwargs():
+    """Pillow's AVIF plugin hands libavif/libaom max_threads = the host's core count for EVERY save(), so a pool of N codec
+    threads spawns N x cores encoder workers per batch; on 256x256 images they only cost (measured, 8 cores, 64 images:
+    0.97 s per batch against 0.36 s with max_threads=2).  The bitstream does not depend on the worker count as long as it
+    is >= 2 (1 switches libaom's row multi-threading off and changes the bytes), which is checked here once per process on
+    a probe image against the default; if the installed libavif ever disagrees, the default stays."""
+    global _AVIF_KW
+    if _AVIF_KW is None:
+        from PIL import Image
+        yy, xx = np.mgrid[0:64, 0:64]
+        probe = np.stack([(xx * 3 + yy * c) % 256 for c in (1, 2, 5)], -1).astype(np.uint8)
+        probe[16:48, 16:48] = 255 - probe[16:48, 16:48]
+        enc = []
+        for kw in ({}, {"max_threads": 2}):
+            buf = io.BytesIO()
+            Image.fromarray(probe).save(buf, format="AVIF", quality=20, **kw)
+            enc.append(buf.getvalue())
+        _AVIF_KW = {"max_threads": 2} if enc[0] == enc[1] else {}
+    return _AVIF_KW
+
+
 def _roundtrip_one(codec, q, src, dst):
     """src, dst: [H, W, 3] uint8 numpy views (dst is written in place)."""
     from PIL import Image
+    t0 = time.perf_counter()
     img = Image.fromarray(src, mode="RGB")
     buf = io.BytesIO()
     if codec == "webp":
         img.save(buf, format="WEBP", quality=q)
     elif codec == "avif":
-        img.save(buf, format="AVIF", quality=q)
+        img.save(buf, format="AVIF", quality=q, **_avif_save_kwargs())
     elif codec == "jpeg":
         img.save(buf, format="JPEG", quality=q, subsampling="4:4:4" if q > 30 else "4:2:0")
     else:
@@ -75,6 +100,7 @@ def _roundtrip_one(codec, q, src, dst):
     if dec.mode != "RGB":
         dec = dec.convert("RGB")
     dst[...] = np.asarray(dec, dtype=np.uint8)
+    CPU_SECONDS[0] += time.perf_counter() - t0     # a float += under the GIL: good enough for a counter
 
 
 def submit_roundtrip(codec, quality, src_u8, dst_u8):
