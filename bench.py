@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--family", default="avif", choices=["avif", "webp", "jpeg"])
+    ap.add_argument("--family", default="avif", choices=["avif", "webp", "jpeg", "mixed"],
+                    help="mixed = BASELINE configs[4]: a third of the batch per codec (JPEG q=10 / WebP q=10 / AVIF q=20), each on its own UNet")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
@@ -49,8 +50,12 @@ def parse():
                          "(--family jpeg only) or the opt-in DCT-domain projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
-                    help="sample = the headline DDRM restoration loop (BASELINE configs[1]); train = BASELINE configs[3], "
+    ap.add_argument("--attn-lin", type=int, default=None, help="tuning: largest polynomial set of the polynomial-kernel attention tier, -1 = off")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the short runs of BASELINE's other configurations that the default N=1 run appends as `secondary`")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "gmm"],
+                    help="sample = the headline DDRM restoration loop (BASELINE configs[1]); gmm = BASELINE configs[2], the SVD-guided "
+                         "GaussianMixtureSampler on a JPEG(q=10) batch; train = BASELINE configs[3], "
                          "one webp_training.py optimizer step per step (WebP UNet 64x64, batch 32/GPU, NCCL gradient all-reduce)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
     return ap.parse_args()
@@ -246,6 +251,239 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ---- per-op accounting (one profiled step): algorithmic bytes / FLOPs of every op class that goes through ops._timed -------
+def op_work(name, tag):
+    """-> ("flops" | "bytes", amount) of one call: the ALGORITHMIC work, not what the kernel moves."""
+    if name in ("conv3x3", "gemm"):
+        B, H, W, K, N = tag
+        return "flops", 2.0 * B * H * W * K * N * (9 if name == "conv3x3" else 1)
+    if name == "attention":
+        B, L, C, heads = tag
+        return "flops", 4.0 * B * float(L) * L * C                 # QK^T + PV of the reference's softmax attention
+    if name == "groupnorm_stats":
+        B, HW, C, es = tag
+        return "bytes", B * HW * C * es
+    if name == "groupnorm_apply":
+        B, HW, C, es, eo = tag
+        return "bytes", B * HW * C * (es + eo)
+    if name == "block_transform":
+        B, HW, C, es, eo = tag
+        return "bytes", B * HW * C * (es + eo)
+    if name == "maxpool2":
+        B, HW, C, es = tag
+        return "bytes", B * HW * C * es * 1.25
+    if name == "upsample2_concat":
+        B, HW, C1, C2, es = tag
+        return "bytes", B * HW * es * (C1 + 4 * C2 + 4 * (C1 + C2))
+    if name == "avgpool_pyramid":
+        B, HW, C, es = tag
+        return "bytes", B * HW * C * es
+    if name == "avif_combine":
+        B, HW, C, eh, ex = tag
+        return "bytes", B * HW * C * (eh + 4 * ex)
+    if name == "conv_input":
+        B, Cin, H, W, N, ks, eo = tag
+        return "bytes", B * H * W * (Cin * 4 + N * eo)
+    if name == "out_conv_tanh":
+        B, HW, Cin, N, es = tag
+        return "bytes", B * HW * (Cin * es + N * 4)
+    if name == "ddrm_update":
+        B, C, H, W, u8 = tag
+        return "bytes", B * C * H * W * (12 + (1 if u8 else 4))
+    if name == "quantize_u8_hwc":
+        B, C, H, W = tag
+        return "bytes", B * C * H * W * 5
+    if name == "svd_lowrank":
+        n, H, W, k = tag
+        return "bytes", n * H * W * 8
+    return "bytes", 0.0
+
+
+def summarize_ops(timed, pk):
+    """{class: {...}} of one profiled step + the list of (op, shape) groups, largest first."""
+    classes, groups = {}, {}
+    for name, lst in timed.items():
+        for ms, tag in lst:
+            kind, amount = op_work(name, tag)
+            c = classes.setdefault(name, {"ms": 0.0, "calls": 0, "kind": kind, "work": 0.0})
+            c["ms"] += ms; c["calls"] += 1; c["work"] += amount
+            g = groups.setdefault((name, tag), {"ms": 0.0, "calls": 0, "kind": kind, "work": 0.0})
+            g["ms"] += ms; g["calls"] += 1; g["work"] += amount
+    for c in list(classes.values()) + list(groups.values()):
+        rate = c["work"] / max(c["ms"], 1e-9) * 1e3
+        if c["kind"] == "flops":
+            c["tflops"] = rate / 1e12
+        else:
+            c["gbs"] = rate / 1e9; c["frac_of_hbm_peak"] = rate / 1e9 / pk["hbm"]
+        del c["work"]
+    return classes, sorted(groups.items(), key=lambda kv: -kv[1]["ms"])
+
+
+def traffic_from_profile(kernel_key):
+    """DRAM bytes per launch of a kernel from an ncu --set full capture, if profiles/ncu_traffic.json has this exact kernel and
+    shape (written by tools/ncu_traffic.py from the .ncu-rep; carries its own provenance).  Never a literal in this file."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.isfile(p):
+        return None, None
+    d = json.load(open(p)).get(kernel_key)
+    return (d["dram_bytes"], d["source"]) if d else (None, None)
+
+
+class SampleJob:
+    """One codec family's share of the batch: model, sampler, synthetic degraded images (host, pinned)."""
+
+    def __init__(self, fam, batch, res, seed, dev, args):
+        import ddpm_image_restoration_b200 as P
+        self.fam, self.q, self.traj = fam, QUALITY[fam], TRAJ_STEPS[fam]
+        model = {"avif": P.AVIFDiffusionModel, "webp": P.WebPDiffusionModel, "jpeg": P.JPEGDiffusionModel}[fam]()
+        self.model = model.to(dev).eval().set_precision("bf16")
+        self.cls = {"avif": P.DDRMAVIFSampler, "webp": P.DDRMWebPSampler, "jpeg": P.DDRMJPEGSampler}[fam]
+        self.y_host = synth_batch(fam, batch, res, seed=seed).pin_memory()
+        self.dev, self.args = dev, args
+
+    def sampler(self):
+        return self.cls(self.model, seed=7, micro_batches=self.args.micro_batches, projection=self.args.projection)
+
+
+def run_sample_steps(job, n_steps, warm, host_io, barrier, timed_filter=None):
+    """Times n_steps timesteps (after `warm` untimed ones) -> (device ms, wall ms, stats).  host_io: the trajectory starts
+    from the pinned host batch and ends with the restored batch copied back to the host (the e2e arm)."""
+    import torch
+    from ddpm_image_restoration_b200 import codec, ops
+    sampler = job.sampler()
+    traj, q, dev, y_host = job.traj, job.q, job.dev, job.y_host
+    st = sampler.begin(y_host.to(dev, non_blocking=True), q, steps=traj)
+    i = traj - 1
+    for _ in range(warm):
+        # the e2e arm starts a fresh trajectory inside the timed region: nothing may be pre-enqueued for it
+        sampler.step(st, i, prefetch=not host_io); i = (i - 1) % traj
+    if host_io:
+        i = traj - 1
+    barrier()
+    ops.LAUNCHES[0] = 0
+    st["h2d"] = st["d2h"] = 0; st["codec_s"] = 0.0
+    codec.CPU_SECONDS[0] = 0.0
+    if timed_filter is not None:
+        ops.timing_begin(timed_filter)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    if host_io:
+        st = sampler.begin(y_host.to(dev, non_blocking=True), q, steps=traj)   # the user-facing call starts from host images
+        st["h2d"] += y_host.numel() * 4
+    for n in range(n_steps):
+        sampler.step(st, i, prefetch=not (host_io and n == n_steps - 1)); i = (i - 1) % traj
+    if host_io:
+        out_host = torch.empty(y_host.shape, dtype=torch.float32, pin_memory=True)
+        out_host.copy_(st["x_t"], non_blocking=True); st["d2h"] += y_host.numel() * 4
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = e0.elapsed_time(e1)
+    timed = ops.timing_end() if timed_filter is not None else {}
+    return ms, wall, dict(launches=ops.LAUNCHES[0], h2d=st["h2d"], d2h=st["d2h"], codec_s=st["codec_s"], timed=timed,
+                          codec_cpu_s=codec.CPU_SECONDS[0], finite=bool(torch.isfinite(st["x_t"]).all()))
+
+
+def profile_one_step(job, barrier):
+    """One sampler timestep with a CUDA-event pair around EVERY op of libddpmir (outside the headline timing)."""
+    import torch
+    from ddpm_image_restoration_b200 import ops
+    sampler = job.sampler()
+    st = sampler.begin(job.y_host.to(job.dev), job.q, steps=job.traj)
+    for i in (job.traj - 1, job.traj - 2):
+        sampler.step(st, i)
+    barrier()
+    ops.timing_begin(lambda name, tag: True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); sampler.step(st, job.traj - 3); e1.record()
+    barrier()
+    return e0.elapsed_time(e1), ops.timing_end()
+
+
+def run_gmm(args, dev, steps_sample=None):
+    """BASELINE configs[2]: the SVD-guided GaussianMixtureSampler (0409_method.ipynb#c1:L390-449) on a JPEG(q=10) batch at
+    256x256, 91 timesteps (init_t + 1), SVD low-rank guide on timesteps i > 45 (rank int(256 * i / 91)), phase consistency every
+    5th step.  A step = one timestep over the batch; timesteps with and without the SVD guide are timed separately and weighted
+    45 : 46 as in the full trajectory (steps_sample = how many of each kind are timed; None = the whole trajectory)."""
+    import torch
+    import ddpm_image_restoration_b200 as P
+    from ddpm_image_restoration_b200 import ops
+    B, res, steps = args.batch, args.res, 91
+    torch.manual_seed(0)
+    model = P.JPEGDiffusionModel().to(dev).eval().set_precision("bf16")
+    y = synth_batch("jpeg", B, res, seed=4321).to(dev)
+    smp = P.GaussianMixtureSampler(model, num_timesteps=100, seed=7)
+    st = smp.begin(y, steps=steps)
+    with_svd = list(range(steps - 1, steps // 2, -1))
+    without = list(range(steps // 2, -1, -1))
+    if steps_sample is not None:
+        with_svd, without = with_svd[:steps_sample], without[:steps_sample]
+    for i in (steps - 1, steps - 2, steps // 2):      # warm-up (both kinds)
+        smp.step(st, i)
+    torch.cuda.synchronize()
+    ops.LAUNCHES[0] = 0
+    ops.timing_begin(lambda name, tag: name == "svd_lowrank")
+    res_ms = {}
+    for kind, lst in (("svd", with_svd), ("plain", without)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in lst:
+            smp.step(st, i)
+        e1.record(); torch.cuda.synchronize()
+        res_ms[kind] = e0.elapsed_time(e1) / len(lst)
+    svd = ops.timing_end().get("svd_lowrank", [])
+    n_svd, n_plain = steps - 1 - steps // 2, steps // 2 + 1
+    traj_ms = n_svd * res_ms["svd"] + n_plain * res_ms["plain"]
+    svd_ms = sum(m for m, _ in svd) / max(1, len(svd))
+    return {"metric": "restored images/sec (256^2, SVD-guided GMM solver)", "value": B / (traj_ms / 1e3), "unit": "images/s",
+            "ms_per_step": traj_ms / steps, "ms_per_step_with_svd": res_ms["svd"], "ms_per_step_without_svd": res_ms["plain"],
+            "svd_ms_per_call": svd_ms, "svd_planes": 3 * B, "svd_share_of_trajectory": n_svd * svd_ms / traj_ms,
+            "steps_timed": len(with_svd) + len(without), "gpu_launches": ops.LAUNCHES[0],
+            "finite": bool(torch.isfinite(st["x_t"]).all()),
+            "config": {"workload": f"0409_method.ipynb GaussianMixtureSampler, JPEG(q=10) batch {B} {res}x{res}, 91 timesteps, "
+                                   "SVD guide on i > 45, phase consistency every 5th step, device JPEG; JPEG UNet of svd.ipynb"}}
+
+
+def run_secondary(args, dev, pk):
+    """Short runs of BASELINE's other configurations, folded into the headline line (each also runs stand-alone:
+    --family webp --batch 1, --workload gmm, --workload train, --family mixed --res 512)."""
+    import copy
+    import torch
+    out = {}
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as e:                      # a secondary line must never take the headline down
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        out[name]["bench_wall_s"] = time.perf_counter() - t0
+        torch.cuda.empty_cache()
+
+    def sample_line(fam, batch, res, k):
+        a = copy.copy(args); a.micro_batches = None if batch < 16 else args.micro_batches
+        fams = ["jpeg", "webp", "avif"] if fam == "mixed" else [fam]
+        tot_img, tot_s, per = 0, 0.0, {}
+        for f in fams:
+            job = SampleJob(f, batch, res, 99, dev, a)
+            ms, _, stt = run_sample_steps(job, k, 3, False, lambda: torch.cuda.synchronize())
+            per[f] = {"ms_per_step": ms / k, "images_per_s": batch / (job.traj * ms / k / 1e3), "finite": stt["finite"]}
+            tot_img += batch; tot_s += job.traj * ms / k / 1e3
+            del job
+            torch.cuda.empty_cache()
+        return {"value": tot_img / tot_s, "unit": "images/s", "per_family": per, "steps_timed": k,
+                "config": {"workload": f"DDRM sampling {fam} batch {batch}/family {res}x{res}"}}
+
+    guarded("config1_webp_q10_256_single_image", lambda: sample_line("webp", 1, 256, 10))
+    def gmm():
+        a = copy.copy(args); a.batch, a.res = 64, 256
+        return run_gmm(a, dev, steps_sample=3)
+    guarded("config3_gmm_svd_jpeg_q10_256_b64", gmm)
+    guarded("config5_mixed_512_b4_per_family", lambda: sample_line("mixed", 4, 512, 3))
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -255,7 +493,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import ddpm_image_restoration_b200 as P
     from ddpm_image_restoration_b200 import codec, ops
 
     rank = int(os.environ.get("RANK", "0"))
@@ -265,91 +502,21 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    fam = args.family
-    traj = TRAJ_STEPS[fam]
-    K = args.steps if args.steps is not None else traj
-    Wm = max(3, args.warmup)
     host_cores = os.cpu_count() or 1
     codec.set_threads(max(1, host_cores // world))
-
     if args.attn_expmode is not None:
         from ddpm_image_restoration_b200 import _lib
         _lib.lib().ddpmir_attention_set_expmode(args.attn_expmode)
-    torch.manual_seed(0)
-    model = {"avif": P.AVIFDiffusionModel, "webp": P.WebPDiffusionModel, "jpeg": P.JPEGDiffusionModel}[fam]()
-    model = model.to(dev).eval().set_precision("bf16")
-    sampler_cls = {"avif": P.DDRMAVIFSampler, "webp": P.DDRMWebPSampler, "jpeg": P.DDRMJPEGSampler}[fam]
-    y_host = synth_batch(fam, args.batch, args.res, seed=1234 + rank).pin_memory()
-    B, C, H, Wd = y_host.shape
-    q = QUALITY[fam]
+    if args.attn_lin is not None:
+        from ddpm_image_restoration_b200 import _lib
+        _lib.lib().ddpmir_attention_set_lin(args.attn_lin)
+    pk = peaks()
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def run(n_steps, warm, host_io):
-        """Times n_steps timesteps (after `warm` untimed ones) -> (device ms, stats).  host_io: the trajectory starts
-        from the pinned host batch and ends with the restored batch copied back to the host (the e2e arm)."""
-        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches, projection=args.projection)
-        y_dev = y_host.to(dev, non_blocking=True)
-        st = sampler.begin(y_dev, q, steps=traj)
-        i = traj - 1
-        for _ in range(warm):
-            # the e2e arm starts a fresh trajectory inside the timed region: nothing may be pre-enqueued for it
-            sampler.step(st, i, prefetch=not host_io); i = (i - 1) % traj
-        if host_io:
-            i = traj - 1
-        barrier()
-        ops.LAUNCHES[0] = 0
-        st["h2d"] = st["d2h"] = 0; st["codec_s"] = 0.0
-        L_full = H * Wd
-        ops.timing_begin(lambda name, tag: name == "attention" and tag[1] == L_full)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record()
-        if host_io:
-            st = sampler.begin(y_host.to(dev, non_blocking=True), q, steps=traj)   # the user-facing call starts from host images
-            st["h2d"] += y_host.numel() * 4
-        for n in range(n_steps):
-            sampler.step(st, i, prefetch=not (host_io and n == n_steps - 1)); i = (i - 1) % traj
-        if host_io:
-            out_host = torch.empty(y_host.shape, dtype=torch.float32, pin_memory=True)
-            out_host.copy_(st["x_t"], non_blocking=True); st["d2h"] += y_host.numel() * 4
-        e1.record()
-        barrier()
-        wall = (time.perf_counter() - t0) * 1e3
-        ms = e0.elapsed_time(e1)
-        attn = ops.timing_end().get("attention", [])
-        return ms, wall, dict(launches=ops.LAUNCHES[0], h2d=st["h2d"], d2h=st["d2h"], codec_s=st["codec_s"], attn=attn,
-                              finite=bool(torch.isfinite(st["x_t"]).all()))
-
-    if args.profile_ops and rank == 0:
-        sampler = sampler_cls(model, seed=7, micro_batches=args.micro_batches, projection=args.projection)
-        st = sampler.begin(y_host.to(dev), q, steps=traj)
-        for i in (traj - 1, traj - 2):
-            sampler.step(st, i)
-        torch.cuda.synchronize()
-        ops.timing_begin(lambda name, tag: True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); sampler.step(st, traj - 3); e1.record()
-        torch.cuda.synchronize()
-        agg = {}
-        for name, lst in ops.timing_end().items():
-            for ms, tag in lst:
-                k = (name, tag)
-                a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += ms
-        tot = sum(v[1] for v in agg.values())
-        print(f"# per-op CUDA-event times of one sampler step ({e0.elapsed_time(e1):.1f} ms total, {tot:.1f} ms in GEMM/conv/attention)", file=sys.stderr)
-        for (name, tag), (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-            print(f"#   {ms:9.3f} ms  x{n:3d}  {name:10s} {tag}", file=sys.stderr)
-
-    clocks = ClockSampler(local)
-    clocks.start()
-    ms, wall, stats = run(K, Wm, host_io=False)
-    clk = clocks.stop()
-    ms_e2e, wall_e2e, stats_e2e = run(K, 1, host_io=True)
 
     def reduce_max(v):
         if world == 1:
@@ -358,61 +525,132 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms = reduce_max(max(ms, 0.0)); ms_e2e = reduce_max(max(wall_e2e, ms_e2e))
-    ms_per_step = ms / K
-    value = world * B / (traj * ms_per_step / 1e3)
-    e2e_value = world * B / (traj * (ms_e2e / K) / 1e3)
+    if args.workload == "gmm":
+        line = run_gmm(args, dev, steps_sample=args.steps)
+        v = torch.tensor([line["value"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            line.update({"value": float(v.item()), "n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                         "dtype": "bf16", "data": "synthetic"})
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    # roofline of the dominant kernel: the full-resolution attention launches (L = H*W tokens)
-    pk = peaks()
-    heads = 8 if fam == "avif" else 4
-    attn = stats["attn"]
-    roof = None
-    if attn:
-        avg_ms = sum(m for m, _ in attn) / len(attn)
-        bsz = attn[0][1][0]
-        flops = 4.0 * (H * Wd) ** 2 * 64 * bsz      # 4 L^2 C per image (QK^T + PV), C = 64 at full resolution
-        ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": f"attn_tc_kernel<hd={64 // heads}> (tcgen05/TMEM bounded-softmax self-attention, full resolution, L={H * Wd})",
-                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                # dram__bytes_read+write of this launch from profiles/r1_attn_tc_ncu_metrics.csv (ncu --set full, same shape)
-                "traffic": 542.1e6 if (fam == "avif" and bsz == 16 and H * Wd == 65536) else None,
-                "algorithmic_bytes": bsz * H * Wd * 64 * 2 * 4,
-                "peak_source": pk["src"] + " (sustained bf16 GEMM)", "launch_ms": avg_ms,
-                "launches_timed": len(attn), "share_of_step": sum(m for m, _ in attn) / ms,
-                "exp_pipe": {"scores_per_s": heads * (H * Wd) ** 2 * bsz / (avg_ms * 1e-3),
-                             "mufu_ceiling_scores_per_s": 16 * 148 * (clk["sm_mhz"] or 1965.0) * 1e6,
-                             "frac": heads * (H * Wd) ** 2 * bsz / (avg_ms * 1e-3) / (16 * 148 * (clk["sm_mhz"] or 1965.0) * 1e6)},
-                "note": "this kernel is bound by the exp (MUFU) + issue pipes, not the tensor pipe: head_dim 8/16 gives 16-32 "
-                        "FLOP per exp.  exp_pipe.frac is against the MUFU-only ceiling (16 exp2/clk/SM); the kernel evaluates "
-                        "every other score pair on the FMA/ALU pipes (packed bf16), so it can exceed 1.  See DESIGN.md section 4 and "
-                        "profiles/r1_ncu_summary.md"}
-    unet_tflops = UNET_GF[fam] * B / 1e3 / (ms_per_step / 1e3) if args.res == 256 else None
+    torch.manual_seed(0)
+    fams = ["jpeg", "webp", "avif"] if args.family == "mixed" else [args.family]
+    per_fam = args.batch // len(fams)
+    jobs = [SampleJob(f, per_fam, args.res, 1234 + rank, dev, args) for f in fams]
+    B_total = per_fam * len(fams)
+    Wm = max(3, args.warmup)
+    H = Wd = args.res
 
+    if args.profile_ops and rank == 0:
+        step_ms, timed = profile_one_step(jobs[-1], barrier)
+        classes, groups = summarize_ops(timed, pk)
+        tot = sum(c["ms"] for c in classes.values())
+        print(f"# per-op CUDA-event times of one sampler step ({step_ms:.1f} ms total, {tot:.1f} ms inside libddpmir ops)", file=sys.stderr)
+        for (name, tag), g_ in groups[:48]:
+            rate = f"{g_['tflops']:8.1f} TFLOP/s" if "tflops" in g_ else f"{g_['gbs']:8.0f} GB/s"
+            print(f"#   {g_['ms']:9.3f} ms  x{g_['calls']:3d}  {rate}  {name:16s} {tag}", file=sys.stderr)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_f, wall_f, stats_f = [], [], []
+    for job in jobs:
+        K = args.steps if args.steps is not None else job.traj
+        ms, wall, stt = run_sample_steps(job, K, Wm, False, barrier)
+        ms_f.append(reduce_max(max(ms, 0.0)) / K); wall_f.append(wall / K); stats_f.append(stt)
+    clk = clocks.stop()
+    e2e_f, stats_e2e = [], []
+    for job in jobs:
+        K = args.steps if args.steps is not None else job.traj
+        ms_e, wall_e, stt = run_sample_steps(job, K, 1, True, barrier)
+        e2e_f.append(reduce_max(max(wall_e, ms_e)) / K); stats_e2e.append(stt)
+    K = args.steps if args.steps is not None else jobs[0].traj
+    # images / second: every family's share of the batch needs traj_f timesteps of ms_f each
+    value = world * B_total / sum(j.traj * m / 1e3 for j, m in zip(jobs, ms_f))
+    e2e_value = world * B_total / sum(j.traj * m / 1e3 for j, m in zip(jobs, e2e_f))
+    ms_per_step = sum(ms_f)
+
+    # one profiled timestep (after the timed runs): every libddpmir op between CUDA events -> roofline objects
+    roof = roof_convs = roof_attn = hbm_table = None
+    if rank == 0:
+        job = jobs[-1]
+        step_ms, timed = profile_one_step(job, lambda: torch.cuda.synchronize())
+        classes, groups = summarize_ops(timed, pk)
+        conv_ms = sum(classes[n]["ms"] for n in ("conv3x3", "gemm") if n in classes)
+        conv_fl = sum(g_["tflops"] * g_["ms"] for (n, _), g_ in groups if n in ("conv3x3", "gemm"))   # TFLOP/s * ms = GFLOP
+        if conv_ms > 0:
+            roof_convs = {"bound": "tensor", "kernel": "igemm_tc_kernel / igemm_tc_stream_kernel (every conv3x3 and 1x1 GEMM of one timestep)",
+                          "achieved": conv_fl / conv_ms, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                          "frac": conv_fl / conv_ms / pk["tf_sustained"], "ms_per_step": conv_ms,
+                          "gflop_per_step": conv_fl, "launches": sum(classes[n]["calls"] for n in ("conv3x3", "gemm") if n in classes)}
+        if "attention" in classes:
+            a = classes["attention"]
+            roof_attn = {"ms_per_step": a["ms"], "launches": a["calls"], "reference_equivalent_tflops": a["tflops"],
+                         "note": "4 L^2 C FLOP of the reference's softmax attention per call / measured time.  With the "
+                                 "polynomial-kernel tier (attn_lin.cu, logit bound <= 2) the arithmetic actually executed is "
+                                 "O(L F head_dim), so this is an equivalent rate, not tensor-pipe utilisation"}
+        hbm_table = {n: {"ms_per_step": c["ms"], "calls": c["calls"], "gbs": c["gbs"], "frac_of_hbm_peak": c["frac_of_hbm_peak"]}
+                     for n, c in classes.items() if c["kind"] == "bytes" and c["ms"] > 0}
+        # the dominant kernel = the (op, shape) group with the most time in the step
+        (dname, dtag), dg = groups[0]
+        key = f"{dname}{list(dtag)}"
+        traffic, tsrc = traffic_from_profile(key)
+        kind, work = op_work(dname, dtag)
+        avg_ms = dg["ms"] / dg["calls"]
+        if kind == "flops":
+            ach = work / (avg_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                    "peak_source": pk["src"] + " (sustained bf16 GEMM)"}
+        else:
+            ach = work / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                    "peak_source": pk["src"] + " (copy bandwidth)"}
+        roof.update({"kernel": key, "launch_ms": avg_ms, "launches_per_step": dg["calls"], "share_of_step": dg["ms"] / step_ms,
+                     "traffic": traffic, "traffic_source": tsrc, "algorithmic_work": work,
+                     "profiled_step_ms": step_ms})
+        if dname == "attention":
+            heads = dtag[3]
+            roof["note"] = ("attention call = pre-pass + polynomial-kernel tier (attn_lin.cu) + quadratic tiers for what it declines; "
+                            "achieved = the reference's 4 L^2 C FLOP / time (an equivalent rate: see roofline_attention.note)")
+
+    unet_tflops = UNET_GF[jobs[0].fam] * B_total / 1e3 / (ms_per_step / 1e3) if (args.res == 256 and len(jobs) == 1) else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fam = jobs[0].fam
         one = cpu_step_seconds(fam, args.res, host_cores)
         s = one()
-        cpu = {"value": 1.0 / (traj * s), "unit": "images/s", "cores": host_cores, "kind": "port",
-               "sample": f"1 image x 1 sampler timestep (UNet fwd + {fam} round trip + update) = {s:.2f} s, x{traj} timesteps"}
+        cpu = {"value": 1.0 / (TRAJ_STEPS[fam] * s), "unit": "images/s", "cores": host_cores, "kind": "port",
+               "sample": f"1 image x 1 sampler timestep (UNet fwd + {fam} round trip + update) = {s:.2f} s, x{TRAJ_STEPS[fam]} timesteps"}
+    secondary = None
+    if rank == 0 and world == 1 and args.secondary and args.family == "avif" and args.res == 256:
+        secondary = run_secondary(args, dev, pk)
 
     if rank == 0:
+        fam_txt = "+".join(f"{j.fam.upper()}(q={j.q})" for j in jobs)
         line = {
-            "metric": "restored images/sec (256^2, full DDPM loop)", "value": value, "unit": "images/s", "n_gpus": world,
+            "metric": "restored images/sec (256^2, full DDPM loop)" if args.res == 256 else f"restored images/sec ({args.res}^2, full DDPM loop)",
+            "value": value, "unit": "images/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{fam}_inference.py DDRM sampling: batch {B}/GPU {fam.upper()}(q={q}) {H}x{Wd}, "
-                                   f"{traj} timesteps/trajectory, step = one timestep over the batch",
-                       "batch_per_gpu": B, "timesteps_per_trajectory": traj, "micro_batches": args.micro_batches,
+            "config": {"workload": f"DDRM sampling ({'/'.join(j.fam for j in jobs)}_inference.py): batch {B_total}/GPU {fam_txt} {H}x{Wd}, "
+                                   f"{'/'.join(str(j.traj) for j in jobs)} timesteps/trajectory, step = one timestep over the batch",
+                       "batch_per_gpu": B_total, "timesteps_per_trajectory": [j.traj for j in jobs], "micro_batches": args.micro_batches,
                        "projection": args.projection,
                        "codec_threads_per_rank": codec.pool_threads(), "host_cores": host_cores,
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": stats_e2e["h2d"] / K,
-                    "d2h_bytes_per_step": stats_e2e["d2h"] / K,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": sum(s_["h2d"] for s_ in stats_e2e) / K,
+                    "d2h_bytes_per_step": sum(s_["d2h"] for s_ in stats_e2e) / K,
                     "note": "DDRM sampler public API from pinned host images to pinned host result; wall clock"},
-            "gpu_launches": stats["launches"], "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": sum(s_["launches"] for s_ in stats_f), "clocks": clk, "roofline": roof, "roofline_convs": roof_convs,
+            "roofline_attention": roof_attn, "hbm_kernels": hbm_table, "cpu_baseline": cpu,
             "unet_tflops": unet_tflops, "unet_frac_of_bf16_sustained": (unet_tflops / pk["tf_sustained"]) if unet_tflops else None,
-            "codec_wait_ms_per_step": stats["codec_s"] * 1e3 / K, "wall_ms_per_step": wall / K, "finite": stats["finite"],
+            "codec_wait_ms_per_step": sum(s_["codec_s"] for s_ in stats_f) * 1e3 / K,
+            "codec_cpu_ms_per_step": sum(s_["codec_cpu_s"] for s_ in stats_f) * 1e3 / K,
+            "wall_ms_per_step": sum(wall_f), "finite": all(s_["finite"] for s_ in stats_f), "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

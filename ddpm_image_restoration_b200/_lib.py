@@ -92,7 +92,7 @@ _SIGNATURES = {
 }
 
 # not part of the public header: tuning hook used by tests/bench
-_PRIVATE = {"ddpmir_attention_set_expmode": (c_int, [c_int]), "ddpmir_igemm_set_variant": (c_int, [c_int])}
+_PRIVATE = {"ddpmir_attention_set_expmode": (c_int, [c_int]), "ddpmir_attention_set_lin": (c_int, [c_int]), "ddpmir_igemm_set_variant": (c_int, [c_int])}
 
 _lib = None
 

@@ -1,0 +1,595 @@
+// Polynomial-kernel tier of the bounded-softmax self-attention (inference, head_dim 8 / 16, binary16 qkv with pre-scaled q).
+//
+// The quadratic tiers (attn_tc16.cu, attn_tc.cu) already evaluate P = 2^s' for most score pairs with a minimax POLYNOMIAL of
+// s' on the FMA pipe -- possible because the Cauchy-Schwarz bound |s'_ij| <= |q'_i| max_j |k_j| keeps every logit of an
+// (image, head) inside a small window.  A polynomial of an inner product is a finite-dimensional kernel:
+//     p(q.k) = sum_n c_n (q.k)^n = sum_n c_n sum_{|a| = n} (n! / a!) q^a k^a          (a = multi-index over the head_dim dims)
+// so with the monomial feature map phi(x) = (x^a)_{|a| <= D}, F = C(head_dim + D, D) features,
+//     sum_j p(s'_ij) [v_j | 1] = phi(q_i) . S ,     S = diag(c_n n!/a!) sum_j phi(k_j) (x) [v_j | 1]      (F x (head_dim + 1))
+// and the whole attention of one (image, head) costs O(L F head_dim) instead of O(L^2 head_dim) multiply-adds and NO
+// exponentials: at L = 65 536, head_dim 8, D = 4 (F = 495) that is 5.8e8 instead of 6.9e10 multiply-adds per head.  The result
+// is the one the quadratic kernels would give with their FMA-pipe polynomial on every pair (same coefficients for the
+// logit window 2); it is NOT an approximation of a different operator ("linear attention"), the softmax weights are the
+// reference's up to the polynomial's relative error, which is chosen per (image, head) from its logit bound:
+//     bound <= 0.5: degree 2 (1.7e-3)   <= 1.0: degree 3 (1.2e-3)   <= 1.5: degree 4 (6.1e-4)   <= 2.0: degree 4 (2.5e-3)
+// (max relative error of one weight; a constant factor cancels in O / l).  (image, head) pairs beyond the window -- trained
+// networks with sharp attention -- are left to the quadratic tiers, exactly as CTAs beyond their windows are handed down there.
+//
+// Three kernels per degree, all SIMT fp32 (this file is the reference implementation of the tier; the features are generated
+// in registers by a depth-first walk over the monomials, one multiply per feature):
+//   attn_lin_state_kernel   grid (splits, heads, B): S partial sums over a slice of the keys (features of 32 keys staged in
+//                           shared memory, every thread owns a few feature rows of S);
+//   attn_lin_reduce_kernel  sums the slices (deterministic order -- no atomics) and applies c_n n!/a!;
+//   attn_lin_out_kernel     thread = query row: walks phi(q_i) against S (shared memory, broadcast reads), divides, writes bf16.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXDEG = 4;
+constexpr int NSETS = 4;
+// minimax polynomials of 2^x in relative error on [-B, B] (tools/minimax_exp2.py)
+__constant__ float c_poly[NSETS][MAXDEG + 1] = {
+    {1.00044314f, 0.703448007f, 0.238428937f, 0.f, 0.f},                          // degree 2, B = 0.5
+    {0.998997116f, 0.694930421f, 0.249528671f, 0.0541850512f, 0.f},               // degree 3, B = 1.0
+    {0.999535858f, 0.691511522f, 0.241847765f, 0.0590221947f, 0.00919362656f},    // degree 4, B = 1.5
+    {0.997719925f, 0.689048622f, 0.24514987f, 0.0614503155f, 0.00887524488f},     // degree 4, B = 2.0
+};
+__host__ __device__ constexpr int set_degree(int s) { return s == 0 ? 2 : s == 1 ? 3 : 4; }
+__host__ __device__ constexpr float set_bound(int s) { return s == 0 ? 0.5f : s == 1 ? 1.0f : s == 2 ? 1.5f : 2.0f; }
+
+__host__ __device__ constexpr long long binom(int n, int k) {
+    if (k < 0 || k > n) return 0;
+    long long r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+// monomials of degree <= deg in n variables
+__host__ __device__ constexpr int nfeat(int n, int deg) { return (int)binom(n + deg, deg); }
+// nodes of the depth-first subtree rooted at "variable d chosen at level lev" (lev = 1 .. DEG): the monomial itself plus
+// every extension by variables >= d up to total degree DEG = monomials of degree <= DEG - lev in HD - d variables
+__host__ __device__ constexpr int subtree(int hd, int deg, int d, int lev) { return nfeat(hd - d, deg - lev); }
+
+// depth-first walk from "first variable d1" (runtime, warp-uniform); x[] in registers, the inner levels are unrolled
+template <int HD, int DEG, typename Emit>
+__device__ __forceinline__ void dfs_from(const float (&x)[HD], int d1, float m1, Emit&& emit) {
+    emit(m1);
+    if constexpr (DEG >= 2) {
+#pragma unroll
+        for (int d2 = 0; d2 < HD; ++d2) {
+            if (d2 < d1) continue;
+            const float m2 = m1 * x[d2];
+            emit(m2);
+            if constexpr (DEG >= 3) {
+#pragma unroll
+                for (int d3 = d2; d3 < HD; ++d3) {
+                    const float m3 = m2 * x[d3];
+                    emit(m3);
+                    if constexpr (DEG >= 4) {
+#pragma unroll
+                        for (int d4 = d3; d4 < HD; ++d4) emit(m3 * x[d4]);
+                    }
+                }
+            }
+        }
+    }
+}
+// position of subtree d1 in the feature order (feature 0 is the constant)
+template <int HD, int DEG> __device__ __forceinline__ int subtree_base(int d1) {
+    int b = 1;
+    for (int d = 0; d < d1; ++d) b += subtree(HD, DEG, d, 1);
+    return b;
+}
+// c_n n!/a! of feature f in the depth-first order
+template <int HD, int DEG> __device__ float feature_coef(int f, const float* c) {
+    if (f == 0) return c[0];
+    int pos = f - 1, lev = 1, start = 0, run = 0, prev = -1;
+    float mult = 1.f;              // n! / a! built incrementally: multiplying by lev / (multiplicity of the chosen variable)
+    for (;;) {
+        int d = start;
+        for (; d < HD; ++d) {
+            const int sz = subtree(HD, DEG, d, lev);
+            if (pos < sz) break;
+            pos -= sz;
+        }
+        run = (d == prev) ? run + 1 : 1;
+        prev = d;
+        mult = mult * (float)lev / (float)run;
+        if (pos == 0) return c[lev] * mult;
+        pos -= 1; lev += 1; start = d;
+    }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+// ---- pre-pass ------------------------------------------------------------------------------------------------------------------
+// The logit window is what decides the polynomial, so the pre-pass makes it as small as exact algebra allows, per (image, head):
+//   * centring:  q_i . k_j = (q_i - a) . (k_j - b) + a . (k_j - b) + q_i . b.  The last term is constant along a softmax row and
+//     cancels; the middle one is a per-KEY weight w_j = 2^(a . (k_j - b)) that multiplies [v_j | 1] in the state sum (one exact
+//     exp2 per key).  a, b = the means of q' and k: feature maps carry a large common component (GroupNorm offsets, biases).
+//   * balancing: (q - a) . (k - b) = (D (q - a)) . (D^-1 (k - b)) for any diagonal D > 0; D_d = sqrt(rms_d(k - b) / rms_d(q - a))
+//     equalises the two factors per dimension, which tightens the Cauchy-Schwarz bound max |D q~| max |D^-1 k~| and keeps the
+//     monomials of both sides in the same range.
+// Both are exact rewrites of the same logits; measured on the bench network they take the bound from 0.9 - 2.9 to 0.6 - 1.9.
+// params per (image, head): a[16] | b[16] | D[16] | 1/D[16]   (head_dim <= 16)
+constexpr int PSTRIDE = 64;
+
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_lin_moments_kernel(const __half* __restrict__ qkv, float* __restrict__ mom, int L, int C, int rows_per_slice) {
+    const int b = blockIdx.z, h = blockIdx.y, slice = blockIdx.x, H = gridDim.y;
+    const long long rstride = 3LL * C;
+    const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
+    const int r0 = slice * rows_per_slice, r1 = min(L, r0 + rows_per_slice);
+    float acc[4][HD];                      // sum q, sum k, sum q^2, sum k^2
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[m][d] = 0.f;
+    for (int j = r0 + threadIdx.x; j < r1; j += 256) {
+        float q[HD], k[HD];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride) + c), q + 8 * c);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride + C) + c), k + 8 * c);
+        }
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { acc[0][d] += q[d]; acc[1][d] += k[d]; acc[2][d] = fmaf(q[d], q[d], acc[2][d]); acc[3][d] = fmaf(k[d], k[d], acc[3][d]); }
+    }
+    __shared__ float red[8][4 * HD];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            const float v = warp_sum(acc[m][d]);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][m * HD + d] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 4 * HD) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        mom[(((long long)(b * H + h)) * gridDim.x + slice) * (4 * HD) + threadIdx.x] = v;
+    }
+}
+
+// every CTA of an (image, head) derives the same a, b, D from the slice moments (fixed summation order), then scans its rows
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_lin_maxima_kernel(const __half* __restrict__ qkv, const float* __restrict__ mom, float* __restrict__ params, float* __restrict__ mx,
+                       int L, int C, int rows_per_slice) {
+    const int b = blockIdx.z, h = blockIdx.y, slice = blockIdx.x, H = gridDim.y, bh = b * H + h;
+    __shared__ float par[PSTRIDE];
+    if (threadIdx.x < HD) {
+        const int d = threadIdx.x;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sl = 0; sl < (int)gridDim.x; ++sl)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) s[m] += mom[((long long)bh * gridDim.x + sl) * (4 * HD) + m * HD + d];
+        const float inv = 1.f / (float)L;
+        const float a = s[0] * inv, bb = s[1] * inv;
+        const float vq = fmaxf(s[2] * inv - a * a, 0.f), vk = fmaxf(s[3] * inv - bb * bb, 0.f);
+        float D = 1.f;
+        if (vq > 1e-12f && vk > 1e-12f) D = sqrtf(sqrtf(vk / vq));
+        D = fminf(fmaxf(D, 1.f / 16.f), 16.f);
+        par[d] = a; par[16 + d] = bb; par[32 + d] = D; par[48 + d] = 1.f / D;
+        if (slice == 0) {
+            float* p = params + (long long)bh * PSTRIDE;
+            p[d] = a; p[16 + d] = bb; p[32 + d] = D; p[48 + d] = 1.f / D;
+        }
+    }
+    __syncthreads();
+    const long long rstride = 3LL * C;
+    const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
+    const int r0 = slice * rows_per_slice, r1 = min(L, r0 + rows_per_slice);
+    float bq = 0.f, bk = 0.f, bk0 = 0.f;       // max |D (q - a)|^2, max |(k - b) / D|^2, max |k|^2 (the quadratic tiers' bound)
+    for (int j = r0 + threadIdx.x; j < r1; j += 256) {
+        float q[HD], k[HD];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride) + c), q + 8 * c);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride + C) + c), k + 8 * c);
+        }
+        float sq = 0.f, sk = 0.f, sk0 = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            const float qd = (q[d] - par[d]) * par[32 + d], kd = (k[d] - par[16 + d]) * par[48 + d];
+            sq = fmaf(qd, qd, sq); sk = fmaf(kd, kd, sk); sk0 = fmaf(k[d], k[d], sk0);
+        }
+        if (!(sq == sq)) sq = __int_as_float(0x7f800000);      // NaN rows must not vanish in fmaxf
+        if (!(sk == sk)) sk = __int_as_float(0x7f800000);
+        if (!(sk0 == sk0)) sk0 = __int_as_float(0x7f800000);
+        bq = fmaxf(bq, sq); bk = fmaxf(bk, sk); bk0 = fmaxf(bk0, sk0);
+    }
+    __shared__ float red[3][8];
+    bq = warp_max(bq); bk = warp_max(bk); bk0 = warp_max(bk0);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = bq; red[1][threadIdx.x >> 5] = bk; red[2][threadIdx.x >> 5] = bk0; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float v = red[threadIdx.x][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) v = fmaxf(v, red[threadIdx.x][w]);
+        mx[((long long)bh * gridDim.x + slice) * 3 + threadIdx.x] = v;
+    }
+}
+
+// logit bound -> polynomial set (or -1: quadratic tiers); kmax for those tiers; zeroes their decline counter
+__global__ void __launch_bounds__(128)
+attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ kmax, int* __restrict__ tier, int* __restrict__ zero_me,
+                       int n_bh, int slices, int max_set, int max_set_hd) {
+    const int bh = blockIdx.x * 128 + threadIdx.x;
+    if (zero_me && bh == 0) *zero_me = 0;
+    if (bh >= n_bh) return;
+    float bq = 0.f, bk = 0.f, bk0 = 0.f;
+    for (int s = 0; s < slices; ++s) {
+        bq = fmaxf(bq, mx[((long long)bh * slices + s) * 3]);
+        bk = fmaxf(bk, mx[((long long)bh * slices + s) * 3 + 1]);
+        bk0 = fmaxf(bk0, mx[((long long)bh * slices + s) * 3 + 2]);
+    }
+    kmax[bh] = sqrtf(bk0);
+    const float bound = sqrtf(bq) * sqrtf(bk) * 1.0001f;
+    int t = -1;
+    const int lim = max_set < max_set_hd ? max_set : max_set_hd;
+    if (bound == bound) {           // NaN -> quadratic tiers (which hand it on to the exact kernel)
+        for (int s = NSETS - 1; s >= 0; --s) if (s <= lim && bound <= set_bound(s)) t = s;
+    }
+    tier[bh] = t;
+}
+
+// ---- S partial sums -----------------------------------------------------------------------------------------------------
+template <int HD, int DEG> struct StateCfg {
+    static constexpr int F = nfeat(HD, DEG);
+    static constexpr int NC = HD + 1;
+    static constexpr int KT = F <= 512 ? 32 : 16;                 // keys per tile (the feature tile must fit shared memory)
+    static constexpr int TPG = F <= 512 ? 128 : 256;              // threads that share one key of the tile in the accumulation phase
+    static constexpr int GROUPS = 256 / TPG;
+    static constexpr int NFT = (F + TPG - 1) / TPG;               // feature rows of S per thread
+    static constexpr int FP = F | 1;                              // odd row stride: the generation phase writes columns
+    static constexpr int VP = (NC + 3) / 4 * 4;
+    static constexpr int TILE_FLOATS = KT * FP + KT * VP + KT * HD;
+    static constexpr size_t SMEM = (size_t)(TILE_FLOATS > F * NC ? TILE_FLOATS : F * NC) * 4;   // the tile, later the [F][NC] reduction buffer
+};
+
+template <int HD, int DEG>
+__global__ void __launch_bounds__(256)
+attn_lin_state_kernel(const __half* __restrict__ qkv, const int* __restrict__ tier, const float* __restrict__ params,
+                      float* __restrict__ spart, int L, int C, int keys_per_split) {
+    using Cfg = StateCfg<HD, DEG>;
+    constexpr int F = Cfg::F, NC = Cfg::NC, KT = Cfg::KT, TPG = Cfg::TPG, GROUPS = Cfg::GROUPS, NFT = Cfg::NFT, FP = Cfg::FP, VP = Cfg::VP;
+    const int b = blockIdx.z, h = blockIdx.y, split = blockIdx.x, H = gridDim.y;
+    const int set = tier[b * H + h];
+    if (set < 0 || set_degree(set) != DEG) return;
+    extern __shared__ __align__(16) float smem_f[];
+    float* phi = smem_f;                     // [KT][FP]
+    float* vs = phi + KT * FP;               // [KT][VP]: w (v | 1) | 0..
+    float* ks = vs + KT * VP;                // [KT][HD]: (k - b) / D
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long rstride = 3LL * C;
+    const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
+    const int j0 = split * keys_per_split, j1 = min(L, j0 + keys_per_split);
+    const float* par = params + (long long)(b * H + h) * PSTRIDE;
+
+    float acc[NFT][NC];
+#pragma unroll
+    for (int i = 0; i < NFT; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[i][c] = 0.f;
+    const int grp = tid / TPG, tg = tid % TPG;
+
+    // thread r < KT stages key r of the tile: its raw k and v rows are fetched one tile ahead (registers), so the global-memory
+    // latency hides behind the feature generation and accumulation of the current tile
+    uint4 kraw[HD / 8], vraw[HD / 8];
+    auto fetch = [&](int jt) {
+        const int j = jt + tid;
+        if (tid < KT && j < j1) {
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                kraw[c] = __ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride + C) + c);
+                vraw[c] = __ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride + 2 * C) + c);
+            }
+        }
+    };
+    fetch(j0);
+    for (int jt = j0; jt < j1; jt += KT) {
+        if (tid < KT) {
+            const bool live = jt + tid < j1;
+            float k[HD], v[HD];
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) { unpack8(kraw[c], k + 8 * c); unpack8(vraw[c], v + 8 * c); }
+            float e = 0.f;                              // a . (k - b): the key's weight 2^e
+#pragma unroll
+            for (int d = 0; d < HD; ++d) {
+                const float kc = live ? k[d] - par[16 + d] : 0.f;
+                e = fmaf(par[d], kc, e);
+                ks[tid * HD + d] = kc * par[48 + d];
+            }
+            const float w = live ? exp2f(e) : 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) vs[tid * VP + d] = w * v[d];
+            vs[tid * VP + HD] = w;
+            phi[tid * FP] = 1.f;                        // the constant feature
+        }
+        __syncthreads();
+        fetch(jt + KT);
+        // features: lane = key, the subtrees (first variable d1) are dealt to the warps
+        if (lane < KT) {
+            float x[HD];
+#pragma unroll
+            for (int d = 0; d < HD; ++d) x[d] = ks[lane * HD + d];
+            float* row = phi + lane * FP;
+            for (int s = warp; s < HD; s += 8) {
+                const int d1 = (HD == 16 && (s & 8)) ? 23 - s : s;   // head_dim 16: warps take d1 = w and 15 - w (balanced)
+                int idx = subtree_base<HD, DEG>(d1);
+                dfs_from<HD, DEG>(x, d1, ks[lane * HD + d1], [&](float m) { row[idx++] = m; });
+            }
+        }
+        __syncthreads();
+        // accumulation: group g takes keys g, g + GROUPS, ...; thread tg of a group owns feature rows tg, tg + TPG, ...
+#pragma unroll 2
+        for (int r = grp; r < KT; r += GROUPS) {
+            float v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[c] = vs[r * VP + c];
+#pragma unroll
+            for (int i = 0; i < NFT; ++i) {
+                const int f = tg + i * TPG;
+                const float p = f < F ? phi[r * FP + f] : 0.f;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fmaf(p, v[c], acc[i][c]);
+            }
+        }
+        __syncthreads();
+    }
+    // combine the key groups through shared memory, then write this split's partial
+    float* red = smem_f;                     // [F][NC]
+    for (int g = 0; g < GROUPS; ++g) {
+        if (grp == g) {
+#pragma unroll
+            for (int i = 0; i < NFT; ++i) {
+                const int f = tg + i * TPG;
+                if (f < F) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) red[f * NC + c] = (g == 0 ? 0.f : red[f * NC + c]) + acc[i][c];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* dst = spart + (((long long)(b * H + h)) * gridDim.x + split) * (F * NC);
+    for (int i = tid; i < F * NC; i += 256) dst[i] = red[i];
+}
+
+// S = coef * (1 / L) * sum over splits, rows padded to NCP floats
+template <int HD, int DEG>
+__global__ void __launch_bounds__(256)
+attn_lin_reduce_kernel(const float* __restrict__ spart, const int* __restrict__ tier, float* __restrict__ S, int splits, float inv_l) {
+    constexpr int F = nfeat(HD, DEG), NC = HD + 1, NCP = (NC + 3) / 4 * 4;
+    const int bh = blockIdx.x;
+    const int set = tier[bh];
+    if (set < 0 || set_degree(set) != DEG) return;
+    const float* src = spart + (long long)bh * splits * (F * NC);
+    float* dst = S + (long long)bh * (F * NCP);
+    for (int f = threadIdx.x; f < F; f += 256) {
+        const float cf = feature_coef<HD, DEG>(f, c_poly[set]) * inv_l;
+        float a[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[c] = 0.f;
+        for (int s = 0; s < splits; ++s)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a[c] += src[(long long)s * (F * NC) + f * NC + c];
+#pragma unroll
+        for (int c = 0; c < NCP; ++c) dst[f * NCP + c] = c < NC ? a[c] * cf : 0.f;
+    }
+}
+
+// ---- output: thread = R query rows -----------------------------------------------------------------------------------------
+template <int HD, int DEG, int R>
+__global__ void __launch_bounds__(256)
+attn_lin_out_kernel(const __half* __restrict__ qkv, const int* __restrict__ tier, const float* __restrict__ params, const float* __restrict__ S,
+                    bf16* __restrict__ out, int* __restrict__ flags, int L, int C) {
+    constexpr int F = nfeat(HD, DEG), NC = HD + 1, NCP = (NC + 3) / 4 * 4;
+    const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+    const int set = tier[b * H + h];
+    if (set < 0 || set_degree(set) != DEG) return;
+    extern __shared__ __align__(16) float smem_f[];
+    float* Ss = smem_f;                      // [F][NCP]
+    float* qs = Ss + F * NCP;                // [R][HD][256]: runtime-indexed reads of the first variable
+    const int tid = threadIdx.x;
+    {
+        const float4* src = reinterpret_cast<const float4*>(S + (long long)(b * H + h) * (F * NCP));
+        float4* dst = reinterpret_cast<float4*>(Ss);
+        for (int i = tid; i < F * NCP / 4; i += 256) dst[i] = __ldg(src + i);
+    }
+    const int row0 = blockIdx.x * (256 * R);
+    // the quadratic tiers skip these rows: their 128-row flags are cleared here
+    if (tid < 2 * R) {
+        const int t128 = blockIdx.x * 2 * R + tid;
+        if (t128 * 128 < L) flags[((long long)(b * H + h)) * ((L + 127) / 128) + t128] = 0;
+    }
+    const long long rstride = 3LL * C;
+    const float* par = params + (long long)(b * H + h) * PSTRIDE;
+    float x[R][HD];
+    int rows[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        rows[r] = row0 + r * 256 + tid;
+        const int rr = min(rows[r], L - 1);
+        const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((long long)b * L + rr) * rstride + (long long)h * HD);
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) unpack8(__ldg(qp + c), &x[r][c * 8]);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            x[r][d] = (x[r][d] - par[d]) * par[32 + d];             // D (q' - a)
+            qs[(r * HD + d) * 256 + tid] = x[r][d];
+        }
+    }
+    __syncthreads();
+    float acc[R][NC];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[r][c] = Ss[c];             // the constant feature
+    // both rows walk the tree together so that one broadcast read of an S row serves R rows
+    const float* srow = Ss + NCP;
+#pragma unroll 1
+    for (int d1 = 0; d1 < HD; ++d1) {
+        float m1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) m1[r] = qs[(r * HD + d1) * 256 + tid];
+        auto emit = [&](const float (&m)[R]) {
+            float s[NCP];
+#pragma unroll
+            for (int c4 = 0; c4 < NCP / 4; ++c4) {
+                const float4 t = *reinterpret_cast<const float4*>(srow + c4 * 4);
+                s[c4 * 4] = t.x; s[c4 * 4 + 1] = t.y; s[c4 * 4 + 2] = t.z; s[c4 * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[r][c] = fmaf(m[r], s[c], acc[r][c]);
+            srow += NCP;
+        };
+        emit(m1);
+        if constexpr (DEG >= 2) {
+#pragma unroll
+            for (int d2 = 0; d2 < HD; ++d2) {
+                if (d2 < d1) continue;
+                float m2[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) m2[r] = m1[r] * x[r][d2];
+                emit(m2);
+                if constexpr (DEG >= 3) {
+#pragma unroll
+                    for (int d3 = d2; d3 < HD; ++d3) {
+                        float m3[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) m3[r] = m2[r] * x[r][d3];
+                        emit(m3);
+                        if constexpr (DEG >= 4) {
+#pragma unroll
+                            for (int d4 = d3; d4 < HD; ++d4) {
+                                float m4[R];
+#pragma unroll
+                                for (int r = 0; r < R; ++r) m4[r] = m3[r] * x[r][d4];
+                                emit(m4);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (rows[r] >= L) continue;
+        const float inv = 1.f / acc[r][HD];
+        bf16* op = out + ((long long)b * L + rows[r]) * C + (long long)h * HD;
+#pragma unroll
+        for (int c8 = 0; c8 < HD / 8; ++c8) {
+            uint4 w;
+            __nv_bfloat162* wp = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wp[i] = __floats2bfloat162_rn(acc[r][c8 * 8 + 2 * i] * inv, acc[r][c8 * 8 + 2 * i + 1] * inv);
+            *reinterpret_cast<uint4*>(op + c8 * 8) = w;
+        }
+    }
+}
+
+int lin_splits(int B, int L, int heads) {
+    int s = 2048 / (B * heads);
+    const int cap = L / 256;
+    if (s > cap) s = cap;
+    return s < 1 ? 1 : s;
+}
+
+constexpr int max_degree(int hd) { return hd == 8 ? 4 : 3; }      // SIMT: 4845 features at head_dim 16, degree 4 cost more than the quadratic tier
+constexpr int max_set_of(int hd) { return hd == 8 ? 3 : 1; }
+
+struct LinWs {              // carved out of the caller's workspace
+    int* tier; float* params; float* mom; float* mx; float* S; float* spart;
+    size_t bytes;
+};
+LinWs carve(void* base, int B, int L, int heads, int hd) {
+    const int F = nfeat(hd, max_degree(hd)), NC = hd + 1, NCP = (NC + 3) / 4 * 4, splits = lin_splits(B, L, heads);
+    const size_t bh = (size_t)B * heads;
+    LinWs w;
+    char* p = (char*)base;
+    auto take = [&](size_t n_floats) { char* r = p; p += (n_floats * 4 + 255) / 256 * 256; return r; };
+    w.tier = (int*)take(bh);
+    w.params = (float*)take(bh * PSTRIDE);
+    w.mom = (float*)take(bh * splits * 4 * hd);
+    w.mx = (float*)take(bh * splits * 3);
+    w.S = (float*)take(bh * F * NCP);
+    w.spart = (float*)take(bh * splits * F * NC);
+    w.bytes = (size_t)(p - (char*)base);
+    return w;
+}
+
+template <int HD, int DEG>
+int launch_degree(const __half* qkv, const LinWs& w, bf16* out, int* flags, int B, int L, int C, int heads, cudaStream_t st) {
+    using Cfg = StateCfg<HD, DEG>;
+    constexpr int F = Cfg::F, NC = HD + 1, NCP = (NC + 3) / 4 * 4, R = 2;
+    const int splits = lin_splits(B, L, heads);
+    const int kps = (ceil_div(L, splits) + Cfg::KT - 1) / Cfg::KT * Cfg::KT;
+    constexpr size_t smem_out = (size_t)(F * NCP + R * HD * 256) * 4;
+    static PerDevice attr_set;
+    if (int& done = attr_set.cur(); !done) {
+        cudaError_t e = cudaFuncSetAttribute(attn_lin_state_kernel<HD, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_lin_out_kernel<HD, DEG, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_out);
+        if (e != cudaSuccess) { ddpmir_set_error("attention_lin: smem opt-in failed: %s", cudaGetErrorString(e)); return DDPMIR_ERR_CUDA; }
+        done = 1;
+    }
+    attn_lin_state_kernel<HD, DEG><<<dim3(splits, heads, B), 256, Cfg::SMEM, st>>>(qkv, w.tier, w.params, w.spart, L, C, kps);
+    DDPMIR_LAUNCH_CHECK();
+    attn_lin_reduce_kernel<HD, DEG><<<B * heads, 256, 0, st>>>(w.spart, w.tier, w.S, splits, 1.f / (float)L);
+    DDPMIR_LAUNCH_CHECK();
+    attn_lin_out_kernel<HD, DEG, R><<<dim3(ceil_div(L, 256 * R), heads, B), 256, smem_out, st>>>(qkv, w.tier, w.params, w.S, out, flags, L, C);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+template <int HD>
+int prepass(const __half* qkv, const LinWs& w, float* kmax, int* declined, int B, int L, int C, int heads, int max_set, cudaStream_t st) {
+    const int slices = lin_splits(B, L, heads), rps = ceil_div(L, slices);
+    attn_lin_moments_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, L, C, rps);
+    DDPMIR_LAUNCH_CHECK();
+    attn_lin_maxima_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, w.params, w.mx, L, C, rps);
+    DDPMIR_LAUNCH_CHECK();
+    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, kmax, w.tier, declined, B * heads, slices, max_set, max_set_of(HD));
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+}  // namespace
+
+// workspace of the tier: verdicts, centring / balancing parameters, pre-pass partials, S and its per-slice partials
+size_t ddpmir_attention_lin_workspace(int B, int L, int C, int heads) {
+    const int hd = C / heads;
+    if (hd != 8 && hd != 16) return 256;
+    return carve(nullptr, B, L, heads, hd).bytes;
+}
+
+// Pre-pass + polynomial tier.  kmax [B*heads] and *declined (zeroed) are the quadratic tiers' inputs; tier_out receives the
+// pointer to the per-(image, head) verdicts (>= 0: done here, the quadratic tiers skip it).  max_set: largest polynomial set
+// allowed (-1 disables the tier: every verdict is -1).
+int ddpmir_attention_lin(const void* qkv, void* out, float* kmax, int* flags, int* declined, void* lin_ws, const int** tier_out,
+                         int B, int L, int C, int heads, int max_set, cudaStream_t st) {
+    const int hd = C / heads;
+    if (hd != 8 && hd != 16) return DDPMIR_ERR_UNSUPPORTED;
+    const LinWs w = carve(lin_ws, B, L, heads, hd);
+    const __half* q = (const __half*)qkv;
+    int rc = hd == 8 ? prepass<8>(q, w, kmax, declined, B, L, C, heads, max_set, st) : prepass<16>(q, w, kmax, declined, B, L, C, heads, max_set, st);
+    if (rc != DDPMIR_OK) return rc;
+    *tier_out = w.tier;
+    if (max_set < 0) return DDPMIR_OK;
+    if (max_set > max_set_of(hd)) max_set = max_set_of(hd);
+#define LD(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_degree<HD, DEG>(q, w, (bf16*)out, flags, B, L, C, heads, st)
+    if (hd == 8) { LD(8, 2); LD(8, 3); LD(8, 4); }
+    else { LD(16, 2); LD(16, 3); }
+#undef LD
+    return rc;
+}

@@ -643,6 +643,7 @@ int g_expmode = -1;   // -1 = auto: mode 3 (25 % of the exps on the FMA pipe) at
 int g_mt = 1;
 int g_poly = -1;      // bounded kernel: score tiles of 8 on the FMA pipe (-1 = auto), +8 = degree-2 instead of degree-3 polynomial
 int g_split16 = 0;    // half-precision tier (attn_tc16.cu): MUFU share of its two FMA-pipe variants, 0 = default
+int g_lin_max_set = 3; // polynomial-kernel tier (attn_lin.cu): largest polynomial set it may use, -1 = tier off
 
 }  // namespace
 
@@ -661,8 +662,17 @@ extern "C" int ddpmir_attention_set_expmode(int mode) {
 
 int ddpmir_attention_simt(const void* qkv, int dtype, int B, int L, int C, int heads, void* out, float qscale, cudaStream_t st);
 int ddpmir_attention_tc(const void* qkv, void* out, const float* kmax, int* flags, int B, int L, int C, int heads, int sel, int redo, cudaStream_t st);
-int ddpmir_attention_tc16(const void* qkv, void* out, const float* kmax, int* flags, int* declined, int B, int L, int C, int heads, int split,
-                          cudaStream_t st);
+int ddpmir_attention_tc16(const void* qkv, void* out, const float* kmax, int* flags, int* declined, const int* skip, int B, int L, int C,
+                          int heads, int split, cudaStream_t st);
+size_t ddpmir_attention_lin_workspace(int B, int L, int C, int heads);
+int ddpmir_attention_lin(const void* qkv, void* out, float* kmax, int* flags, int* declined, void* lin_ws, const int** tier_out,
+                         int B, int L, int C, int heads, int max_set, cudaStream_t st);
+
+// test / tuning hook: largest polynomial set of the polynomial-kernel tier (0..3, see attn_lin.cu), -1 switches the tier off
+extern "C" int ddpmir_attention_set_lin(int max_set) {
+    g_lin_max_set = max_set < -1 ? -1 : max_set > 3 ? 3 : max_set;
+    return DDPMIR_OK;
+}
 
 static int attention_mma_scaled(const void* qkv, int B, int L, int C, int heads, void* out, float* lse, float scale_log2, const int* redo,
                                 bool force_mt1, cudaStream_t st) {
@@ -784,7 +794,7 @@ inline size_t f16_header_bytes(int B, int L, int heads) {
 }  // namespace
 
 extern "C" size_t ddpmir_attention_prescaled_f16_workspace(int B, int L, int C, int heads) {
-    return f16_header_bytes(B, L, heads) + (size_t)B * L * 3 * C * 2;
+    return f16_header_bytes(B, L, heads) + ddpmir_attention_lin_workspace(B, L, C, heads) + (size_t)B * L * 3 * C * 2;
 }
 
 extern "C" int ddpmir_attention_prescaled_f16(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
@@ -801,12 +811,15 @@ extern "C" int ddpmir_attention_prescaled_f16(const void* qkv, int B, int L, int
     float* kmax = (float*)workspace;
     int* flags = (int*)(kmax + (size_t)B * heads);
     int* declined = flags + (size_t)B * heads * ceil_div(L, 128);
-    void* copy = (char*)workspace + f16_header_bytes(B, L, heads);
-    if (hd == 8) attn_kbound_kernel<8, true><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C, declined);
-    else attn_kbound_kernel<16, true><<<dim3(heads, B), 256, 0, st>>>((const bf16*)qkv, kmax, L, C, declined);
-    DDPMIR_LAUNCH_CHECK();
+    void* lin_ws = (char*)workspace + f16_header_bytes(B, L, heads);
+    void* copy = (char*)lin_ws + ddpmir_attention_lin_workspace(B, L, C, heads);
+    // pre-pass (max |q'|, max |k| per image and head) + tier 0: (image, head) pairs whose logit bound is <= 2 are computed through
+    // the polynomial feature map in O(L) (attn_lin.cu); tier[] >= 0 marks them and the kernels below skip their CTAs
+    const int* tier = nullptr;
+    int rc = ddpmir_attention_lin(qkv, out, kmax, flags, declined, lin_ws, &tier, B, L, C, heads, g_lin_max_set, st);
+    if (rc != DDPMIR_OK) return rc;
     // tier 1: S and P in binary16, logit bound <= 11
-    int rc = ddpmir_attention_tc16(qkv, out, kmax, flags, declined, B, L, C, heads, g_split16, st);
+    rc = ddpmir_attention_tc16(qkv, out, kmax, flags, declined, tier, B, L, C, heads, g_split16, st);
     if (rc != DDPMIR_OK) return rc;
     // tiers 2 and 3 read bf16: a copy made only if some CTA was declined (the kernels below return at once otherwise)
     const long long n8 = (long long)B * L * 3 * C / 8;

@@ -99,7 +99,9 @@ template <int NM> __device__ __forceinline__ constexpr bool on_mufu(int i) {
 template <int HD, int NM0, int NM1, int NWG, int CTAS>
 __global__ void __launch_bounds__((NWG * 5 + 1) * 32, CTAS)
 attn_tc16_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ out, const float* __restrict__ kmax, int* __restrict__ flags,
-                 int* __restrict__ declined, int L, int C) {
+                 int* __restrict__ declined, const int* __restrict__ skip, int L, int C) {
+    // (image, head) pairs the polynomial-kernel tier (attn_lin.cu) has computed: nothing to do (it cleared their flags)
+    if (skip && skip[blockIdx.z * gridDim.y + blockIdx.y] >= 0) return;
     constexpr int KB = HD / 8;
     constexpr int NO = HD == 8 ? 16 : 32;       // PV accumulator columns: head_dim | ones | zero padding
     constexpr int TMEM_COLS = 512 / CTAS;
@@ -339,7 +341,8 @@ attn_tc16_kernel(const __grid_constant__ CUtensorMap tmap, bf16* __restrict__ ou
 }
 
 template <int HD, int NM0, int NM1, int NWG, int CTAS>
-int launch16g(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int* declined, int B, int L, int C, int heads, cudaStream_t st) {
+int launch16g(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int* declined, const int* skip, int B, int L, int C, int heads,
+              cudaStream_t st) {
     constexpr int NO = HD == 8 ? 16 : 32;
     constexpr int NSTAGE = nstage(NWG);
     constexpr int need = NSTAGE * (2 + NO / 8) * BLK + 2 * QBLK + (2 * NSTAGE + 4 * NWG + 2) * 8 + 16 + 128;
@@ -354,7 +357,7 @@ int launch16g(const CUtensorMap& tm, void* out, const float* kmax, int* flags, i
         done = 1;
     }
     dim3 grid(L / TQ, heads, B);
-    kern<<<grid, NTHREADS, smem, st>>>(tm, (bf16*)out, kmax, flags, declined, L, C);
+    kern<<<grid, NTHREADS, smem, st>>>(tm, (bf16*)out, kmax, flags, declined, skip, L, C);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -363,11 +366,11 @@ int launch16g(const CUtensorMap& tm, void* out, const float* kmax, int* flags, i
 // at L = 65 536 (72.9 vs 72.1 ms) and loses below (4.89 vs 4.67 ms at L = 16 384): the kernel is bound by issue slots per
 // score, not by the number of warps the schedulers can pick from -- see profiles/r2_ncu_summary.md
 template <int HD, int NM0, int NM1>
-int launch16(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int* declined, int B, int L, int C, int heads, int geom,
-             cudaStream_t st) {
+int launch16(const CUtensorMap& tm, void* out, const float* kmax, int* flags, int* declined, const int* skip, int B, int L, int C, int heads,
+             int geom, cudaStream_t st) {
     const bool wide = geom == 2;
-    return wide ? launch16g<HD, NM0, NM1, 5, 1>(tm, out, kmax, flags, declined, B, L, C, heads, st)
-                : launch16g<HD, NM0, NM1, 2, 2>(tm, out, kmax, flags, declined, B, L, C, heads, st);
+    return wide ? launch16g<HD, NM0, NM1, 5, 1>(tm, out, kmax, flags, declined, skip, B, L, C, heads, st)
+                : launch16g<HD, NM0, NM1, 2, 2>(tm, out, kmax, flags, declined, skip, B, L, C, heads, st);
 }
 
 }  // namespace
@@ -377,8 +380,8 @@ int launch16(const CUtensorMap& tm, void* out, const float* kmax, int* flags, in
 // (tuning hook): MUFU share of the two FMA-pipe variants in eighths, bits 0-2 = bound <= 2 (degree-4 polynomial; 7 =
 // everything on MUFU), bits 3-5 = bound <= 11 (range-reduced); 0 = default.  Bits 6-7: CTA geometry, 2 = one CTA of five
 // warpgroups, otherwise two CTAs of two warpgroups per SM.
-int ddpmir_attention_tc16(const void* qkv, void* out, const float* kmax, int* flags, int* declined, int B, int L, int C, int heads, int split,
-                          cudaStream_t st) {
+int ddpmir_attention_tc16(const void* qkv, void* out, const float* kmax, int* flags, int* declined, const int* skip, int B, int L, int C,
+                          int heads, int split, cudaStream_t st) {
     const int hd = C / heads;
     if ((hd != 8 && hd != 16) || L % TQ != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return DDPMIR_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
@@ -395,13 +398,13 @@ int ddpmir_attention_tc16(const void* qkv, void* out, const float* kmax, int* fl
         if (r != CUDA_SUCCESS) { ddpmir_set_error("attention_tc16: tensor map failed (%d)", (int)r); return DDPMIR_ERR_CUDA; }
     }
     const int nm0 = split & 7, nm1 = (split >> 3) & 7, geom = (split >> 6) & 3;
-#define L16(HD) (nm0 == 2 ? launch16<HD, 2, 4>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st) : \
-                 nm0 == 4 ? launch16<HD, 4, 4>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st) : \
-                 nm0 == 5 ? launch16<HD, 5, 4>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st) : \
-                 nm0 == 7 ? launch16<HD, 8, 8>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st) : \
-                 nm1 == 3 ? launch16<HD, 3, 3>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st) : \
-                 nm1 == 5 ? launch16<HD, 3, 5>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st) : \
-                            launch16<HD, 3, 4>(tm, out, kmax, flags, declined, B, L, C, heads, geom, st))
+#define L16(HD) (nm0 == 2 ? launch16<HD, 2, 4>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st) : \
+                 nm0 == 4 ? launch16<HD, 4, 4>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st) : \
+                 nm0 == 5 ? launch16<HD, 5, 4>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st) : \
+                 nm0 == 7 ? launch16<HD, 8, 8>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st) : \
+                 nm1 == 3 ? launch16<HD, 3, 3>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st) : \
+                 nm1 == 5 ? launch16<HD, 3, 5>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st) : \
+                            launch16<HD, 3, 4>(tm, out, kmax, flags, declined, skip, B, L, C, heads, geom, st))
     return hd == 8 ? L16(8) : L16(16);
 #undef L16
 }

@@ -90,11 +90,11 @@ def ddrm_update(x_theta, codec, y, t, sigma_scale, eta=0.85, eta_b=1.0, z=None, 
     if not u8:
         _f32(codec, "codec")
     out = torch.empty_like(x_theta) if out is None else out
-    rc = _lib.lib().ddpmir_ddrm_update(_p(x_theta), _p(codec), int(u8), _p(y), _p(z), _p(t), _p(out), B, C, H, W,
-                                       float(sigma_scale), float(eta), float(eta_b), int(last_step), int(seed),
-                                       int(step), int(noise_offset), _stream())
+    with _timed("ddrm_update", (B, C, H, W, int(u8)), 1):
+        rc = _lib.lib().ddpmir_ddrm_update(_p(x_theta), _p(codec), int(u8), _p(y), _p(z), _p(t), _p(out), B, C, H, W,
+                                           float(sigma_scale), float(eta), float(eta_b), int(last_step), int(seed),
+                                           int(step), int(noise_offset), _stream())
     _lib.check(rc, "ddrm_update")
-    LAUNCHES[0] += 1
     return out
 
 
@@ -176,8 +176,8 @@ def u8_hwc_to_nchw(u8):
 def quantize_u8_hwc(x, out=None):
     B, C, H, W = x.shape
     out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device) if out is None else out
-    _lib.check(_lib.lib().ddpmir_quantize_u8_hwc(_p(_f32(x, "x")), _p(out), B, C, H, W, _stream()), "quantize_u8_hwc")
-    LAUNCHES[0] += 1
+    with _timed("quantize_u8_hwc", (B, C, H, W), 1):
+        _lib.check(_lib.lib().ddpmir_quantize_u8_hwc(_p(_f32(x, "x")), _p(out), B, C, H, W, _stream()), "quantize_u8_hwc")
     return out
 
 
@@ -205,9 +205,9 @@ def svd_lowrank(x, k, sweeps=0):
     B, C, H, W = x.shape
     out = torch.empty_like(x)
     ws = torch.empty((B * C * (H * W + H * H + 2 * H),), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().ddpmir_svd_lowrank(_p(_f32(x, "x")), B * C, H, W, int(k), _p(out), _p(ws), int(sweeps), _stream()),
-               "svd_lowrank")
-    LAUNCHES[0] += 1
+    with _timed("svd_lowrank", (B * C, H, W, int(k)), 1):
+        _lib.check(_lib.lib().ddpmir_svd_lowrank(_p(_f32(x, "x")), B * C, H, W, int(k), _p(out), _p(ws), int(sweeps), _stream()),
+                   "svd_lowrank")
     return out
 
 
@@ -283,9 +283,9 @@ def linear_rows(x, w, bias, act=ACT_NONE, out=None):
         out = torch.empty((rows, N), dtype=torch.float32, device=x.device)
     elif out.numel() != rows * N or out.dtype != torch.float32:
         raise _lib.DdpmirError("linear_rows: bad out tensor")
-    _lib.check(_lib.lib().ddpmir_linear_rows(_p(_f32(x, "x")), rows, K, _p(_f32(w, "w")), _p(bias), N, act, _p(out),
-                                             _stream()), "linear_rows")
-    LAUNCHES[0] += 1
+    with _timed("linear_rows", (rows, K, N), 1):
+        _lib.check(_lib.lib().ddpmir_linear_rows(_p(_f32(x, "x")), rows, K, _p(_f32(w, "w")), _p(bias), N, act, _p(out),
+                                                 _stream()), "linear_rows")
     return out
 
 
@@ -298,9 +298,9 @@ def groupnorm_stats(x, groups, eps=1e-5, nchw=False):
         HW = H * W
     mr = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
     ws = torch.empty((B * groups * 2,), dtype=torch.float64, device=x.device)
-    _lib.check(_lib.lib().ddpmir_groupnorm_stats(_p(x), _code(x.dtype), int(nchw), B, HW, C, groups, float(eps), _p(mr),
-                                                 _p(ws), _stream()), "groupnorm_stats")
-    LAUNCHES[0] += 2
+    with _timed("groupnorm_stats", (B, HW, C, x.element_size()), 2):
+        _lib.check(_lib.lib().ddpmir_groupnorm_stats(_p(x), _code(x.dtype), int(nchw), B, HW, C, groups, float(eps), _p(mr),
+                                                     _p(ws), _stream()), "groupnorm_stats")
     return mr
 
 
@@ -310,10 +310,10 @@ def groupnorm_apply(x, mean_rstd, gamma, beta, act=ACT_NONE, out_dtype=None, raw
     out_dtype = x.dtype if out_dtype is None else out_dtype
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     raw = torch.empty(x.shape, dtype=out_dtype, device=x.device) if raw_copy else None
-    _lib.check(_lib.lib().ddpmir_groupnorm_apply(_p(x), _code(x.dtype), B, H * W, C, mean_rstd.shape[1], _p(mean_rstd),
-                                                 _p(gamma), _p(beta), act, _p(out), _code(out_dtype), _p(raw), _stream()),
-               "groupnorm_apply")
-    LAUNCHES[0] += 1
+    with _timed("groupnorm_apply", (B, H * W, C, x.element_size(), out.element_size() * (2 if raw_copy else 1)), 1):
+        _lib.check(_lib.lib().ddpmir_groupnorm_apply(_p(x), _code(x.dtype), B, H * W, C, mean_rstd.shape[1], _p(mean_rstd),
+                                                     _p(gamma), _p(beta), act, _p(out), _code(out_dtype), _p(raw), _stream()),
+                   "groupnorm_apply")
     return (out, raw) if raw_copy else out
 
 
@@ -321,10 +321,10 @@ def conv_input(x, w, bias, out_dtype, mean_rstd=None, gamma=None, beta=None, row
     B, Cin, H, W = x.shape
     N, ks = w.shape[0], w.shape[-1]
     out = torch.empty((B, H, W, N), dtype=out_dtype, device=x.device)
-    _lib.check(_lib.lib().ddpmir_conv_input(_p(_f32(x, "x")), B, Cin, H, W, _p(mean_rstd), _p(gamma), _p(beta), _p(_f32(w, "w")),
-                                            _p(bias), _p(row_bias), N, ks, _code(out_dtype), _p(out), _stream()),
-               "conv_input")
-    LAUNCHES[0] += 1
+    with _timed("conv_input", (B, Cin, H, W, N, ks, out.element_size()), 1):
+        _lib.check(_lib.lib().ddpmir_conv_input(_p(_f32(x, "x")), B, Cin, H, W, _p(mean_rstd), _p(gamma), _p(beta), _p(_f32(w, "w")),
+                                                _p(bias), _p(row_bias), N, ks, _code(out_dtype), _p(out), _stream()),
+                   "conv_input")
     return out
 
 
@@ -419,18 +419,18 @@ def block_transform(x, T, alpha=0.0, beta=1.0, out_dtype=None):
     bs = T.shape[-1]
     out_dtype = x.dtype if out_dtype is None else out_dtype
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    _lib.check(_lib.lib().ddpmir_block_transform(_p(x), _code(x.dtype), B, H, W, C, _p(_f32(T, "T")), bs, int(T.dim() == 3),
-                                                 float(alpha), float(beta), _p(out), _code(out_dtype), _stream()),
-               "block_transform")
-    LAUNCHES[0] += 1
+    with _timed("block_transform", (B, H * W, C, x.element_size(), out.element_size()), 1):
+        _lib.check(_lib.lib().ddpmir_block_transform(_p(x), _code(x.dtype), B, H, W, C, _p(_f32(T, "T")), bs, int(T.dim() == 3),
+                                                     float(alpha), float(beta), _p(out), _code(out_dtype), _stream()),
+                   "block_transform")
     return out
 
 
 def maxpool2(x):
     B, H, W, C = x.shape
     out = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().ddpmir_maxpool2(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "maxpool2")
-    LAUNCHES[0] += 1
+    with _timed("maxpool2", (B, H * W, C, x.element_size()), 1):
+        _lib.check(_lib.lib().ddpmir_maxpool2(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "maxpool2")
     return out
 
 
@@ -438,17 +438,17 @@ def upsample2_concat(lo, skip):
     B, H, W, C1 = lo.shape
     C2 = skip.shape[-1]
     out = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=lo.dtype, device=lo.device)
-    _lib.check(_lib.lib().ddpmir_upsample2_concat(_p(lo), _p(skip), _code(lo.dtype), B, H, W, C1, C2, _p(out), _stream()),
-               "upsample2_concat")
-    LAUNCHES[0] += 1
+    with _timed("upsample2_concat", (B, H * W, C1, C2, lo.element_size()), 1):
+        _lib.check(_lib.lib().ddpmir_upsample2_concat(_p(lo), _p(skip), _code(lo.dtype), B, H, W, C1, C2, _p(out), _stream()),
+                   "upsample2_concat")
     return out
 
 
 def avgpool_pyramid(x):
     B, H, W, C = x.shape
     out = torch.empty((85, B, C), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().ddpmir_avgpool_pyramid(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "avgpool_pyramid")
-    LAUNCHES[0] += 2
+    with _timed("avgpool_pyramid", (B, H * W, C, x.element_size()), 2):
+        _lib.check(_lib.lib().ddpmir_avgpool_pyramid(_p(x), _code(x.dtype), B, H, W, C, _p(out), _stream()), "avgpool_pyramid")
     return out
 
 
@@ -456,9 +456,9 @@ def avif_combine(h, xt, gates, color, edge):
     """h may be the fp32 stream while xt/color/edge (and the result) are in the operand dtype."""
     B, H, W, C = h.shape
     out = torch.empty(h.shape, dtype=xt.dtype, device=h.device)
-    _lib.check(_lib.lib().ddpmir_avif_combine(_p(h), _code(h.dtype), _p(xt), _p(_f32(gates, "gates")), _p(color), _p(edge),
-                                              _code(xt.dtype), B, H, W, C, _p(out), _stream()), "avif_combine")
-    LAUNCHES[0] += 1
+    with _timed("avif_combine", (B, H * W, C, h.element_size(), xt.element_size()), 1):
+        _lib.check(_lib.lib().ddpmir_avif_combine(_p(h), _code(h.dtype), _p(xt), _p(_f32(gates, "gates")), _p(color), _p(edge),
+                                                  _code(xt.dtype), B, H, W, C, _p(out), _stream()), "avif_combine")
     return out
 
 
@@ -466,9 +466,9 @@ def out_conv_tanh(x, w, bias):
     B, H, W, Cin = x.shape
     N = w.shape[0]
     out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().ddpmir_out_conv_tanh(_p(x), _code(x.dtype), B, H, W, Cin, _p(_f32(w, "w")), _p(bias), N, _p(out),
-                                               _stream()), "out_conv_tanh")
-    LAUNCHES[0] += 1
+    with _timed("out_conv_tanh", (B, H * W, Cin, N, x.element_size()), 1):
+        _lib.check(_lib.lib().ddpmir_out_conv_tanh(_p(x), _code(x.dtype), B, H, W, Cin, _p(_f32(w, "w")), _p(bias), N, _p(out),
+                                                   _stream()), "out_conv_tanh")
     return out
 
 

@@ -208,34 +208,44 @@ class GaussianMixtureSampler:
         self.noise_fn = noise_fn
         self.coin_fn = coin_fn
 
-    def sample(self, x_t, steps=100, use_phase_consistency=True, use_svd_guide=True, guidance_scale=1.0):
+    def begin(self, x_t, steps=100, use_phase_consistency=True, use_svd_guide=True, guidance_scale=1.0):
+        """Set up one trajectory; returns the mutable state that step() advances (bench.py times single steps)."""
         if not x_t.is_cuda:
             raise RuntimeError("the B200 sampler runs on CUDA only (no CPU fallback)")
         self.model.eval()
-        dev = x_t.device
         x_t = x_t.contiguous().float().clone()
         y = x_t.clone()
-        B = x_t.shape[0]
-        phasor = ops.phase_reference(y) if use_phase_consistency else None
+        return dict(x_t=x_t, y=y, steps=steps, use_phase=use_phase_consistency, use_svd=use_svd_guide, scale=guidance_scale,
+                    phasor=ops.phase_reference(y) if use_phase_consistency else None)
+
+    def step(self, st, i):
+        """One timestep i (steps-1 ... 0) of 0409_method.ipynb#c1:L406-447 over the whole batch."""
+        x_t, y, steps = st["x_t"], st["y"], st["steps"]
+        B, dev = x_t.shape[0], x_t.device
         with torch.no_grad():
-            for i in range(steps - 1, -1, -1):
-                t = torch.full((B,), float(i) / self.num_timesteps, dtype=torch.float32, device=dev)
-                pred = self.model(x_t, t, t)
-                prior, g = None, 0.0
-                if use_svd_guide and i > steps // 2:
-                    k_ratio = i / steps
-                    prior = svd_structure_preservation(x_t, k_ratio)
-                    g = k_ratio * 0.3
-                if i > 0:
-                    p_cons = max(0.2, min(0.8, i / steps))
-                    # the reference draws torch.rand(1) from the CPU generator (0409_method.ipynb#c1:L432)
-                    coin = self.coin_fn(i) if self.coin_fn is not None else torch.rand(1).item()
-                    z = self.noise_fn(i, x_t).contiguous() if self.noise_fn is not None else None
-                    x_n = ops.gmm_update(x_t, pred, y, prior, g, z=z, use_first=coin < p_cons,
-                                         noise_scale=0.1 * i / steps * guidance_scale, seed=self.seed, step=i)
-                    if use_phase_consistency and i % 5 == 0:
-                        x_n = ops.phase_consistency_cached(x_n, phasor, 0.6 + 0.3 * (1 - i / steps))
-                    x_t = x_n
-                else:
-                    x_t = ops.gmm_update(x_t, pred, y, prior, g, last_step=True)
-        return x_t
+            t = torch.full((B,), float(i) / self.num_timesteps, dtype=torch.float32, device=dev)
+            pred = self.model(x_t, t, t)
+            prior, g = None, 0.0
+            if st["use_svd"] and i > steps // 2:
+                k_ratio = i / steps
+                prior = svd_structure_preservation(x_t, k_ratio)
+                g = k_ratio * 0.3
+            if i > 0:
+                p_cons = max(0.2, min(0.8, i / steps))
+                # the reference draws torch.rand(1) from the CPU generator (0409_method.ipynb#c1:L432)
+                coin = self.coin_fn(i) if self.coin_fn is not None else torch.rand(1).item()
+                z = self.noise_fn(i, x_t).contiguous() if self.noise_fn is not None else None
+                x_n = ops.gmm_update(x_t, pred, y, prior, g, z=z, use_first=coin < p_cons,
+                                     noise_scale=0.1 * i / steps * st["scale"], seed=self.seed, step=i)
+                if st["use_phase"] and i % 5 == 0:
+                    x_n = ops.phase_consistency_cached(x_n, st["phasor"], 0.6 + 0.3 * (1 - i / steps))
+                st["x_t"] = x_n
+            else:
+                st["x_t"] = ops.gmm_update(x_t, pred, y, prior, g, last_step=True)
+        return st["x_t"]
+
+    def sample(self, x_t, steps=100, use_phase_consistency=True, use_svd_guide=True, guidance_scale=1.0):
+        st = self.begin(x_t, steps, use_phase_consistency, use_svd_guide, guidance_scale)
+        for i in range(steps - 1, -1, -1):
+            self.step(st, i)
+        return st["x_t"]

@@ -239,7 +239,11 @@ int ddpmir_attention_prescaled(const void* qkv, int B, int L, int C, int heads, 
  * logit bound: <= 11 (exp2 domain) scores and probabilities stay in binary16 on the tensor cores (attn_tc16.cu); <= 60
  * bf16 probabilities (attn_tc.cu); beyond that the exact online-maximum kernel.  workspace:
  * ddpmir_attention_prescaled_f16_workspace(B, L, C, heads) bytes (flags + room for a bf16 copy of qkv that is written
- * only when a tile leaves the first tier). */
+ * only when a tile leaves the first tier).
+ * Tier 0, ahead of those three and chosen per (image, head): when the logit bound max_i |q'_i| * max_j |k_j| is <= 2, the
+ * softmax weights are evaluated with a minimax polynomial of the logit (degree 2-4, relative error <= 2.5e-3 per weight, the
+ * same polynomial the quadratic tiers use on the FMA pipe) THROUGH ITS MONOMIAL FEATURE MAP, which turns the attention of
+ * that (image, head) into two O(L) contractions instead of an O(L^2) one (attn_lin.cu). */
 size_t ddpmir_attention_prescaled_f16_workspace(int B, int L, int C, int heads);
 int ddpmir_attention_prescaled_f16(const void* qkv, int B, int L, int C, int heads, void* workspace, void* out,
                                    ddpmir_stream_t stream);

@@ -436,10 +436,12 @@ def test_attention_half_precision_tier(ops, hd, heads, L, scale, split):
     pre, ref = _prescaled(torch.randn(2, L, 3 * C, generator=g(hd + L)) * scale, heads, dtype=torch.float16)
     assert pre.dtype == ops.qkv_dtype_for_attention(L, hd)
     _lib.lib().ddpmir_attention_set_expmode(split << 16)
+    _lib.lib().ddpmir_attention_set_lin(-1)                   # the polynomial-kernel tier would take these (image, head) pairs
     try:
         out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
     finally:
         _lib.lib().ddpmir_attention_set_expmode(-1)
+        _lib.lib().ddpmir_attention_set_lin(3)
     want = _attn_ref(ref, heads)
     assert rel(out, want) < 4e-3
     # the bf16 entry point (bf16 tier) on the same values
@@ -472,7 +474,70 @@ def test_attention_tiers_mixed_in_one_launch(ops):
     assert rel(out[1, 1280:1408], want_bf[1, 1280:1408]) < 1e-2
 
 
-@pytest.mark.parametrize("scale", [0.35, 0.8, 1.2])     # logit bound ~2 (a fresh UNet) / ~9 / ~20: the three bounded tiers
+def _logit_bound(pre, heads):
+    """Per (image, head): the logit bound of the polynomial-kernel tier's pre-pass (attn_lin.cu) -- Cauchy-Schwarz after centring
+    q' and k on their means and balancing the two factors per dimension, max_i |D (q'_i - a)| * max_j |(k_j - b) / D|."""
+    B, L, C3 = pre.shape
+    C = C3 // 3
+    q = pre[..., :C].float().view(B, L, heads, -1)
+    k = pre[..., C:2 * C].float().view(B, L, heads, -1)
+    qc, kc = q - q.mean(1, keepdim=True), k - k.mean(1, keepdim=True)
+    D = ((kc * kc).mean(1, keepdim=True) / (qc * qc).mean(1, keepdim=True)).pow(0.25).clamp(1 / 16, 16)
+    return (qc * D).norm(dim=-1).amax(1) * (kc / D).norm(dim=-1).amax(1)
+
+
+@pytest.mark.parametrize("target", [0.45, 0.95, 1.45, 1.95])      # logit bound -> polynomial set 0 (degree 2), 1 (3), 2 and 3 (4)
+@pytest.mark.parametrize("hd,heads,L", [(8, 8, 2048), (8, 4, 1152), (16, 4, 1024), (16, 8, 4096)])
+def test_attention_polynomial_kernel_tier(ops, hd, heads, L, target):
+    """attn_lin.cu: (image, head) pairs whose logit bound is <= 2 are evaluated through the monomial feature map of the minimax
+    polynomial of 2^s (two O(L) contractions).  Checked against float64 softmax with a zero-mean V (the output is then the small
+    position-dependent part of the attention, nothing hides behind a mean) and against the quadratic half-precision tier."""
+    from ddpm_image_restoration_b200 import _lib
+    C = hd * heads
+    qkv = torch.randn(2, L, 3 * C, generator=g(hd + L)) * 0.3
+    qkv[..., :2 * C] += torch.randn(1, 1, 2 * C, generator=g(7)) * 0.2     # q and k with a common component, as feature maps have
+    pre, ref = _prescaled(qkv, heads, dtype=torch.float16)
+    gain = target / float(_logit_bound(pre, heads).max())      # scale q so that the largest (image, head) bound hits the target
+    pre, ref = _prescaled(qkv, heads, gain=gain, dtype=torch.float16)
+    assert float(_logit_bound(pre, heads).max()) < target * 1.02
+    out = ops.attention_prescaled(pre.cuda(), heads).double().cpu()
+    _lib.lib().ddpmir_attention_set_lin(-1)
+    try:
+        quad = ops.attention_prescaled(pre.cuda(), heads).double().cpu()
+    finally:
+        _lib.lib().ddpmir_attention_set_lin(3)
+    want = _attn_ref(ref.double(), heads)
+    r, rq = rel(out, want), rel(quad, want)
+    print(f"polynomial-kernel tier hd={hd} L={L} bound={target}: rel-L2 vs fp64 = {r:.3e} (quadratic tier: {rq:.3e})")
+    bounds = _logit_bound(pre, heads)
+    lim = 2.0 if hd == 8 else 1.0                               # head_dim 16 stops at degree 3 (window 1) in this build
+    if float(bounds.min()) > lim * 1.05:
+        assert torch.equal(out, quad)                           # every (image, head) declined: the quadratic tiers' result
+    elif float(bounds.min()) < lim * 0.95:
+        assert not torch.equal(out, quad)                       # the tier really ran
+    assert r < 6e-3
+
+
+def test_attention_polynomial_kernel_tier_mixed(ops):
+    """One launch, three regimes: most (image, head) pairs through the polynomial kernel, one head with a logit bound of ~6
+    (half-precision quadratic tier), one row with a bound > 60 (exact kernel)."""
+    hd, heads, L = 8, 8, 2048
+    C = hd * heads
+    qkv = torch.randn(2, L, 3 * C, generator=g(17)) * 0.3
+    qkv[0, :, 3 * hd:4 * hd] *= 4.0        # q of head 3, image 0
+    qkv[1, 777, :hd] *= 600.0               # one query row of head 0, image 1
+    pre, ref = _prescaled(qkv, heads, dtype=torch.float16)
+    b = _logit_bound(pre, heads)
+    assert (b <= 2.0).sum() == 2 * heads - 2 and 2.0 < b[0, 3] < 11.0 and b[1, 0] > 60.0
+    out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    want = _attn_ref(ref, heads)
+    assert torch.isfinite(out).all()
+    assert rel(out, want) < 6e-3
+    for (bi, h) in ((0, 3), (1, 0), (0, 0), (1, 7)):
+        assert rel(out[bi, :, h * hd:(h + 1) * hd], want[bi, :, h * hd:(h + 1) * hd]) < 1e-2, (bi, h)
+
+
+@pytest.mark.parametrize("scale", [0.2, 0.35, 0.8, 1.2])     # logit bound ~1 / ~2 (a fresh UNet) / ~9 / ~20: polynomial tier and the three bounded tiers
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("hd,heads", [(8, 8), (16, 4)])
 def test_attention_full_resolution_vs_fp64_rows(ops, hd, heads, dtype, scale):

@@ -13,6 +13,8 @@ B = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 if len(sys.argv) > 5:
     _lib.lib().ddpmir_attention_set_expmode(int(sys.argv[5]))
 pre = len(sys.argv) > 6 and int(sys.argv[6]) == 1
+if "ATTN_LIN" in os.environ:      # largest polynomial set of the polynomial-kernel tier (attn_lin.cu), -1 = tier off
+    _lib.lib().ddpmir_attention_set_lin(int(os.environ["ATTN_LIN"]))
 attn = ops.attention_prescaled if pre else ops.attention
 C = hd * heads
 scale = float(os.environ.get("ATTN_SCALE", "1.0"))   # 0.35: logit bound < 2, 0.8: < 11 (half-precision tiers), 1.0+: bf16 tier
