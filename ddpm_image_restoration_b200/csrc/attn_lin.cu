@@ -24,29 +24,11 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "attn_lin.cuh"
 
 namespace {
+using namespace attn_lin;
 
-constexpr int MAXDEG = 4;
-constexpr int NSETS = 4;
-// minimax polynomials of 2^x in relative error on [-B, B] (tools/minimax_exp2.py)
-__constant__ float c_poly[NSETS][MAXDEG + 1] = {
-    {1.00044314f, 0.703448007f, 0.238428937f, 0.f, 0.f},                          // degree 2, B = 0.5
-    {0.998997116f, 0.694930421f, 0.249528671f, 0.0541850512f, 0.f},               // degree 3, B = 1.0
-    {0.999535858f, 0.691511522f, 0.241847765f, 0.0590221947f, 0.00919362656f},    // degree 4, B = 1.5
-    {0.997719925f, 0.689048622f, 0.24514987f, 0.0614503155f, 0.00887524488f},     // degree 4, B = 2.0
-};
-__host__ __device__ constexpr int set_degree(int s) { return s == 0 ? 2 : s == 1 ? 3 : 4; }
-__host__ __device__ constexpr float set_bound(int s) { return s == 0 ? 0.5f : s == 1 ? 1.0f : s == 2 ? 1.5f : 2.0f; }
-
-__host__ __device__ constexpr long long binom(int n, int k) {
-    if (k < 0 || k > n) return 0;
-    long long r = 1;
-    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
-    return r;
-}
-// monomials of degree <= deg in n variables
-__host__ __device__ constexpr int nfeat(int n, int deg) { return (int)binom(n + deg, deg); }
 // nodes of the depth-first subtree rooted at "variable d chosen at level lev" (lev = 1 .. DEG): the monomial itself plus
 // every extension by variables >= d up to total degree DEG = monomials of degree <= DEG - lev in HD - d variables
 __host__ __device__ constexpr int subtree(int hd, int deg, int d, int lev) { return nfeat(hd - d, deg - lev); }
@@ -82,8 +64,8 @@ template <int HD, int DEG> __device__ __forceinline__ int subtree_base(int d1) {
     return b;
 }
 // c_n n!/a! of feature f in the depth-first order
-template <int HD, int DEG> __device__ float feature_coef(int f, const float* c) {
-    if (f == 0) return c[0];
+template <int HD, int DEG> __device__ float feature_coef(int f, int set) {
+    if (f == 0) return set_coef(set, 0);
     int pos = f - 1, lev = 1, start = 0, run = 0, prev = -1;
     float mult = 1.f;              // n! / a! built incrementally: multiplying by lev / (multiplicity of the chosen variable)
     for (;;) {
@@ -96,7 +78,7 @@ template <int HD, int DEG> __device__ float feature_coef(int f, const float* c) 
         run = (d == prev) ? run + 1 : 1;
         prev = d;
         mult = mult * (float)lev / (float)run;
-        if (pos == 0) return c[lev] * mult;
+        if (pos == 0) return set_coef(set, lev) * mult;
         pos -= 1; lev += 1; start = d;
     }
 }
@@ -115,8 +97,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 //     equalises the two factors per dimension, which tightens the Cauchy-Schwarz bound max |D q~| max |D^-1 k~| and keeps the
 //     monomials of both sides in the same range.
 // Both are exact rewrites of the same logits; measured on the bench network they take the bound from 0.9 - 2.9 to 0.6 - 1.9.
-// params per (image, head): a[16] | b[16] | D[16] | 1/D[16]   (head_dim <= 16)
-constexpr int PSTRIDE = 64;
+// params per (image, head): attn_lin.cuh (a | b | D | 1/D | exponent offset of the key weights)
 
 template <int HD>
 __global__ void __launch_bounds__(256)
@@ -163,7 +144,7 @@ __global__ void __launch_bounds__(256)
 attn_lin_maxima_kernel(const __half* __restrict__ qkv, const float* __restrict__ mom, float* __restrict__ params, float* __restrict__ mx,
                        int L, int C, int rows_per_slice) {
     const int b = blockIdx.z, h = blockIdx.y, slice = blockIdx.x, H = gridDim.y, bh = b * H + h;
-    __shared__ float par[PSTRIDE];
+    __shared__ float par[64];
     if (threadIdx.x < HD) {
         const int d = threadIdx.x;
         float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -187,6 +168,7 @@ attn_lin_maxima_kernel(const __half* __restrict__ qkv, const float* __restrict__
     const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
     const int r0 = slice * rows_per_slice, r1 = min(L, r0 + rows_per_slice);
     float bq = 0.f, bk = 0.f, bk0 = 0.f;       // max |D (q - a)|^2, max |(k - b) / D|^2, max |k|^2 (the quadratic tiers' bound)
+    float emax = -3.0e38f;                     // max a . (k - b): the exponent offset of the key weights
     for (int j = r0 + threadIdx.x; j < r1; j += 256) {
         float q[HD], k[HD];
 #pragma unroll
@@ -194,50 +176,61 @@ attn_lin_maxima_kernel(const __half* __restrict__ qkv, const float* __restrict__
             unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride) + c), q + 8 * c);
             unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)j * rstride + C) + c), k + 8 * c);
         }
-        float sq = 0.f, sk = 0.f, sk0 = 0.f;
+        float sq = 0.f, sk = 0.f, sk0 = 0.f, e = 0.f;
 #pragma unroll
         for (int d = 0; d < HD; ++d) {
             const float qd = (q[d] - par[d]) * par[32 + d], kd = (k[d] - par[16 + d]) * par[48 + d];
             sq = fmaf(qd, qd, sq); sk = fmaf(kd, kd, sk); sk0 = fmaf(k[d], k[d], sk0);
+            e = fmaf(par[d], k[d] - par[16 + d], e);
         }
+        emax = fmaxf(emax, e);
         if (!(sq == sq)) sq = __int_as_float(0x7f800000);      // NaN rows must not vanish in fmaxf
         if (!(sk == sk)) sk = __int_as_float(0x7f800000);
         if (!(sk0 == sk0)) sk0 = __int_as_float(0x7f800000);
         bq = fmaxf(bq, sq); bk = fmaxf(bk, sk); bk0 = fmaxf(bk0, sk0);
     }
-    __shared__ float red[3][8];
-    bq = warp_max(bq); bk = warp_max(bk); bk0 = warp_max(bk0);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = bq; red[1][threadIdx.x >> 5] = bk; red[2][threadIdx.x >> 5] = bk0; }
+    __shared__ float red[4][8];
+    bq = warp_max(bq); bk = warp_max(bk); bk0 = warp_max(bk0); emax = warp_max(emax);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = bq; red[1][threadIdx.x >> 5] = bk; red[2][threadIdx.x >> 5] = bk0; red[3][threadIdx.x >> 5] = emax;
+    }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 4) {
         float v = red[threadIdx.x][0];
 #pragma unroll
         for (int w = 1; w < 8; ++w) v = fmaxf(v, red[threadIdx.x][w]);
-        mx[((long long)bh * gridDim.x + slice) * 3 + threadIdx.x] = v;
+        mx[((long long)bh * gridDim.x + slice) * 4 + threadIdx.x] = v;
     }
 }
 
-// logit bound -> polynomial set (or -1: quadratic tiers); kmax for those tiers; zeroes their decline counter
+// logit bound -> polynomial set (or -1: quadratic tiers); kmax for those tiers; zeroes their decline counter.  Also the last,
+// scalar, step of the balancing: D <- g D with g = sqrt(max |k~/D| / max |D q~|), so that both factors of the bound are equal
+// (= sqrt(bound)) and every monomial of either side stays below sqrt(bound)^degree -- binary16-safe in the tensor-core kernels.
 __global__ void __launch_bounds__(128)
-attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ kmax, int* __restrict__ tier, int* __restrict__ zero_me,
-                       int n_bh, int slices, int max_set, int max_set_hd) {
+attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ params, float* __restrict__ kmax, int* __restrict__ tier,
+                       int* __restrict__ zero_me, int n_bh, int slices, int hd, int max_set) {
     const int bh = blockIdx.x * 128 + threadIdx.x;
     if (zero_me && bh == 0) *zero_me = 0;
     if (bh >= n_bh) return;
-    float bq = 0.f, bk = 0.f, bk0 = 0.f;
+    float bq = 0.f, bk = 0.f, bk0 = 0.f, emax = -3.0e38f;
     for (int s = 0; s < slices; ++s) {
-        bq = fmaxf(bq, mx[((long long)bh * slices + s) * 3]);
-        bk = fmaxf(bk, mx[((long long)bh * slices + s) * 3 + 1]);
-        bk0 = fmaxf(bk0, mx[((long long)bh * slices + s) * 3 + 2]);
+        const float* m = mx + ((long long)bh * slices + s) * 4;
+        bq = fmaxf(bq, m[0]); bk = fmaxf(bk, m[1]); bk0 = fmaxf(bk0, m[2]); emax = fmaxf(emax, m[3]);
     }
     kmax[bh] = sqrtf(bk0);
-    const float bound = sqrtf(bq) * sqrtf(bk) * 1.0001f;
+    const float nq = sqrtf(bq), nk = sqrtf(bk);
+    const float bound = nq * nk * 1.0001f;
     int t = -1;
-    const int lim = max_set < max_set_hd ? max_set : max_set_hd;
-    if (bound == bound) {           // NaN -> quadratic tiers (which hand it on to the exact kernel)
-        for (int s = NSETS - 1; s >= 0; --s) if (s <= lim && bound <= set_bound(s)) t = s;
+    if (bound == bound && emax == emax && fabsf(emax) < 100.f) {           // NaN / absurd -> quadratic tiers (which hand it on to the exact kernel)
+        for (int s = NSETS - 1; s >= 0; --s) if (s <= max_set && bound <= set_bound(s)) t = s;
     }
     tier[bh] = t;
+    float* p = params + (long long)bh * PSTRIDE;
+    if (t >= 0 && nq > 1e-20f && nk > 1e-20f) {
+        const float g = sqrtf(nk / nq);
+        for (int d = 0; d < hd; ++d) { p[P_D + d] *= g; p[P_DI + d] /= g; }
+    }
+    p[P_EOFF] = emax;
 }
 
 // ---- S partial sums -----------------------------------------------------------------------------------------------------
@@ -307,7 +300,7 @@ attn_lin_state_kernel(const __half* __restrict__ qkv, const int* __restrict__ ti
                 e = fmaf(par[d], kc, e);
                 ks[tid * HD + d] = kc * par[48 + d];
             }
-            const float w = live ? exp2f(e) : 0.f;
+            const float w = live ? exp2f(e - par[P_EOFF]) : 0.f;
 #pragma unroll
             for (int d = 0; d < HD; ++d) vs[tid * VP + d] = w * v[d];
             vs[tid * VP + HD] = w;
@@ -374,7 +367,7 @@ attn_lin_reduce_kernel(const float* __restrict__ spart, const int* __restrict__ 
     const float* src = spart + (long long)bh * splits * (F * NC);
     float* dst = S + (long long)bh * (F * NCP);
     for (int f = threadIdx.x; f < F; f += 256) {
-        const float cf = feature_coef<HD, DEG>(f, c_poly[set]) * inv_l;
+        const float cf = feature_coef<HD, DEG>(f, set) * inv_l;
         float a[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) a[c] = 0.f;
@@ -506,25 +499,28 @@ int lin_splits(int B, int L, int heads) {
     return s < 1 ? 1 : s;
 }
 
-constexpr int max_degree(int hd) { return hd == 8 ? 4 : 3; }      // SIMT: 4845 features at head_dim 16, degree 4 cost more than the quadratic tier
-constexpr int max_set_of(int hd) { return hd == 8 ? 3 : 1; }
+// SIMT path: head_dim 8 up to degree 4 (set 3), head_dim 16 up to degree 3 (set 1): beyond that the fp32 accumulation costs more
+// than the quadratic tier.  Tensor-core path (attn_lin_tc.cu): head_dim 8 up to degree 6 (set 5), head_dim 16 up to degree 4 (set 3).
+constexpr int simt_max_set(int hd) { return hd == 8 ? 3 : 1; }
+constexpr int tc_max_set(int hd) { return hd == 8 ? 5 : 3; }
 
 struct LinWs {              // carved out of the caller's workspace
-    int* tier; float* params; float* mom; float* mx; float* S; float* spart;
+    int* tier; float* params; float* mom; float* mx; float* S; float* spart; void* tc;
     size_t bytes;
 };
-LinWs carve(void* base, int B, int L, int heads, int hd) {
-    const int F = nfeat(hd, max_degree(hd)), NC = hd + 1, NCP = (NC + 3) / 4 * 4, splits = lin_splits(B, L, heads);
+LinWs carve(void* base, int B, int L, int C, int heads, int hd) {
+    const int F = nfeat(hd, set_degree(simt_max_set(hd))), NC = hd + 1, NCP = (NC + 3) / 4 * 4, splits = lin_splits(B, L, heads);
     const size_t bh = (size_t)B * heads;
     LinWs w;
     char* p = (char*)base;
-    auto take = [&](size_t n_floats) { char* r = p; p += (n_floats * 4 + 255) / 256 * 256; return r; };
-    w.tier = (int*)take(bh);
-    w.params = (float*)take(bh * PSTRIDE);
-    w.mom = (float*)take(bh * splits * 4 * hd);
-    w.mx = (float*)take(bh * splits * 3);
-    w.S = (float*)take(bh * F * NCP);
-    w.spart = (float*)take(bh * splits * F * NC);
+    auto take = [&](size_t n_bytes) { char* r = p; p += (n_bytes + 255) / 256 * 256; return r; };
+    w.tier = (int*)take(bh * 4);
+    w.params = (float*)take(bh * PSTRIDE * 4);
+    w.mom = (float*)take(bh * splits * 4 * hd * 4);
+    w.mx = (float*)take(bh * splits * 4 * 4);
+    w.S = (float*)take(bh * F * NCP * 4);
+    w.spart = (float*)take(bh * splits * F * NC * 4);
+    w.tc = take(ddpmir_attention_lin_tc_workspace(B, L, hd, heads));
     w.bytes = (size_t)(p - (char*)base);
     return w;
 }
@@ -559,7 +555,7 @@ int prepass(const __half* qkv, const LinWs& w, float* kmax, int* declined, int B
     DDPMIR_LAUNCH_CHECK();
     attn_lin_maxima_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, w.params, w.mx, L, C, rps);
     DDPMIR_LAUNCH_CHECK();
-    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, kmax, w.tier, declined, B * heads, slices, max_set, max_set_of(HD));
+    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, w.params, kmax, w.tier, declined, B * heads, slices, HD, max_set);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -570,26 +566,28 @@ int prepass(const __half* qkv, const LinWs& w, float* kmax, int* declined, int B
 size_t ddpmir_attention_lin_workspace(int B, int L, int C, int heads) {
     const int hd = C / heads;
     if (hd != 8 && hd != 16) return 256;
-    return carve(nullptr, B, L, heads, hd).bytes;
+    return carve(nullptr, B, L, C, heads, hd).bytes;
 }
 
 // Pre-pass + polynomial tier.  kmax [B*heads] and *declined (zeroed) are the quadratic tiers' inputs; tier_out receives the
 // pointer to the per-(image, head) verdicts (>= 0: done here, the quadratic tiers skip it).  max_set: largest polynomial set
-// allowed (-1 disables the tier: every verdict is -1).
+// allowed (-1 disables the tier: every verdict is -1); simt != 0 takes the fp32 SIMT kernels instead of the tcgen05 ones.
 int ddpmir_attention_lin(const void* qkv, void* out, float* kmax, int* flags, int* declined, void* lin_ws, const int** tier_out,
-                         int B, int L, int C, int heads, int max_set, cudaStream_t st) {
+                         int B, int L, int C, int heads, int max_set, int simt, cudaStream_t st) {
     const int hd = C / heads;
     if (hd != 8 && hd != 16) return DDPMIR_ERR_UNSUPPORTED;
-    const LinWs w = carve(lin_ws, B, L, heads, hd);
+    const LinWs w = carve(lin_ws, B, L, C, heads, hd);
     const __half* q = (const __half*)qkv;
+    const int cap = simt ? simt_max_set(hd) : tc_max_set(hd);
+    if (max_set > cap) max_set = cap;
     int rc = hd == 8 ? prepass<8>(q, w, kmax, declined, B, L, C, heads, max_set, st) : prepass<16>(q, w, kmax, declined, B, L, C, heads, max_set, st);
     if (rc != DDPMIR_OK) return rc;
     *tier_out = w.tier;
     if (max_set < 0) return DDPMIR_OK;
-    if (max_set > max_set_of(hd)) max_set = max_set_of(hd);
+    if (!simt) return ddpmir_attention_lin_tc(qkv, out, w.tier, w.params, w.tc, flags, B, L, C, heads, max_set, st);
 #define LD(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_degree<HD, DEG>(q, w, (bf16*)out, flags, B, L, C, heads, st)
-    if (hd == 8) { LD(8, 2); LD(8, 3); LD(8, 4); }
-    else { LD(16, 2); LD(16, 3); }
+    if (hd == 8) { LD(8, 3); LD(8, 4); }
+    else { LD(16, 3); }
 #undef LD
     return rc;
 }

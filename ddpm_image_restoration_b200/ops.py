@@ -389,19 +389,28 @@ def qkv_dtype_for_attention(L, head_dim):
     return torch.float16 if head_dim in (8, 16) and L >= 1024 and L % 128 == 0 else torch.bfloat16
 
 
-def attention_prescaled(qkv, heads):
+def attention_tiers(ws, B, L, heads):
+    """Verdicts of the polynomial-kernel tier inside a workspace of ddpmir_attention_prescaled_f16 (tests / tools): int32 [B, heads],
+    -1 = left to the quadratic tiers, 0..5 = polynomial set (attn_lin.cuh).  The verdicts sit right behind the header
+    (kmax [B*heads] | flags [B*heads*ceil(L/128)] | 4 ints, rounded up to 256 bytes)."""
+    hdr = ((B * heads + B * heads * ((L + 127) // 128) + 4) * 4 + 255) // 256 * 256
+    return ws[hdr:hdr + B * heads * 4].view(torch.int32).view(B, heads).clone()
+
+
+def attention_prescaled(qkv, heads, return_tiers=False):
     """qkv [B, L, 3C] whose q third already carries log2(e)/sqrt(head_dim) -> bf16 [B, L, C].  bf16 qkv: bounded / exact
-    kernels of any shape; binary16 qkv (see qkv_dtype_for_attention): the three-tier path for head_dim 8/16, L >= 1024."""
+    kernels of any shape; binary16 qkv (see qkv_dtype_for_attention): the tiered path for head_dim 8/16, L >= 1024."""
     B, L, C3 = qkv.shape
     C = C3 // 3
     if qkv.dtype == torch.float16:
         out = torch.empty((B, L, C), dtype=torch.bfloat16, device=qkv.device)
         nbytes = _lib.lib().ddpmir_attention_prescaled_f16_workspace(B, L, C, heads)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=qkv.device)
-        with _timed("attention", (B, L, C, heads), 5):   # key norms, f16 tier, conditional bf16 copy, bf16 tier, exact redo
+        # pre-pass (3), polynomial tier (3 per degree in use), f16 tier, conditional bf16 copy, bf16 tier, exact redo
+        with _timed("attention", (B, L, C, heads), 10):
             _lib.check(_lib.lib().ddpmir_attention_prescaled_f16(_p(qkv), B, L, C, heads, _p(ws), _p(out), _stream()),
                        "attention_prescaled_f16")
-        return out
+        return (out, attention_tiers(ws, B, L, heads)) if return_tiers else out
     if qkv.dtype != torch.bfloat16:
         raise TypeError("attention_prescaled is the bf16 / binary16 inference path")
     out = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)

@@ -441,7 +441,7 @@ def test_attention_half_precision_tier(ops, hd, heads, L, scale, split):
         out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
     finally:
         _lib.lib().ddpmir_attention_set_expmode(-1)
-        _lib.lib().ddpmir_attention_set_lin(3)
+        _lib.lib().ddpmir_attention_set_lin(5)
     want = _attn_ref(ref, heads)
     assert rel(out, want) < 4e-3
     # the bf16 entry point (bf16 tier) on the same values
@@ -486,12 +486,13 @@ def _logit_bound(pre, heads):
     return (qc * D).norm(dim=-1).amax(1) * (kc / D).norm(dim=-1).amax(1)
 
 
-@pytest.mark.parametrize("target", [0.45, 0.95, 1.45, 1.95])      # logit bound -> polynomial set 0 (degree 2), 1 (3), 2 and 3 (4)
+@pytest.mark.parametrize("simt", [0, 16])                                      # tcgen05 kernels (attn_lin_tc.cu) / fp32 SIMT kernels (attn_lin.cu)
+@pytest.mark.parametrize("target", [0.7, 0.95, 1.45, 1.95, 2.45, 3.4])         # logit bound -> polynomial set 0 .. 5 (degree 3, 3, 4, 4, 5, 6)
 @pytest.mark.parametrize("hd,heads,L", [(8, 8, 2048), (8, 4, 1152), (16, 4, 1024), (16, 8, 4096)])
-def test_attention_polynomial_kernel_tier(ops, hd, heads, L, target):
-    """attn_lin.cu: (image, head) pairs whose logit bound is <= 2 are evaluated through the monomial feature map of the minimax
-    polynomial of 2^s (two O(L) contractions).  Checked against float64 softmax with a zero-mean V (the output is then the small
-    position-dependent part of the attention, nothing hides behind a mean) and against the quadratic half-precision tier."""
+def test_attention_polynomial_kernel_tier(ops, hd, heads, L, target, simt):
+    """attn_lin*.cu: (image, head) pairs whose logit bound fits a polynomial set are evaluated through the monomial feature map of
+    the minimax polynomial of 2^s (two O(L) contractions).  Checked against float64 softmax with a zero-mean V (the output is then
+    the small position-dependent part of the attention, nothing hides behind a mean) and against the quadratic half-precision tier."""
     from ddpm_image_restoration_b200 import _lib
     C = hd * heads
     qkv = torch.randn(2, L, 3 * C, generator=g(hd + L)) * 0.3
@@ -500,21 +501,28 @@ def test_attention_polynomial_kernel_tier(ops, hd, heads, L, target):
     gain = target / float(_logit_bound(pre, heads).max())      # scale q so that the largest (image, head) bound hits the target
     pre, ref = _prescaled(qkv, heads, gain=gain, dtype=torch.float16)
     assert float(_logit_bound(pre, heads).max()) < target * 1.02
-    out = ops.attention_prescaled(pre.cuda(), heads).double().cpu()
-    _lib.lib().ddpmir_attention_set_lin(-1)
+    _lib.lib().ddpmir_attention_set_lin(5 + simt)
     try:
+        out, tiers = ops.attention_prescaled(pre.cuda(), heads, return_tiers=True)
+        _lib.lib().ddpmir_attention_set_lin(-1)
         quad = ops.attention_prescaled(pre.cuda(), heads).double().cpu()
     finally:
-        _lib.lib().ddpmir_attention_set_lin(3)
+        _lib.lib().ddpmir_attention_set_lin(5)
+    out, tiers = out.double().cpu(), tiers.cpu()
     want = _attn_ref(ref.double(), heads)
     r, rq = rel(out, want), rel(quad, want)
-    print(f"polynomial-kernel tier hd={hd} L={L} bound={target}: rel-L2 vs fp64 = {r:.3e} (quadratic tier: {rq:.3e})")
+    print(f"polynomial-kernel tier ({'SIMT' if simt else 'tcgen05'}) hd={hd} L={L} bound={target}: sets {sorted(set(tiers.flatten().tolist()))}, "
+          f"rel-L2 vs fp64 = {r:.3e} (quadratic tier: {rq:.3e})")
+    # the verdicts must be the smallest window that holds each (image, head) bound, capped by what this build has kernels for:
+    # tcgen05 head_dim 8 -> set 5 (window 3.5), 16 -> set 3 (2.0); SIMT head_dim 8 -> set 3, 16 -> set 1 (1.0)
+    windows = [0.75, 1.0, 1.5, 2.0, 2.5, 3.5]
+    cap = {(0, 8): 5, (0, 16): 3, (16, 8): 3, (16, 16): 1}[(simt, hd)]
     bounds = _logit_bound(pre, heads)
-    lim = 2.0 if hd == 8 else 1.0                               # head_dim 16 stops at degree 3 (window 1) in this build
-    if float(bounds.min()) > lim * 1.05:
-        assert torch.equal(out, quad)                           # every (image, head) declined: the quadratic tiers' result
-    elif float(bounds.min()) < lim * 0.95:
-        assert not torch.equal(out, quad)                       # the tier really ran
+    for bnd, t in zip(bounds.flatten().tolist(), tiers.flatten().tolist()):
+        ok = [s for s in range(cap + 1) if bnd * 0.999 <= windows[s]]
+        near_edge = any(abs(bnd - w) < 0.01 * w for w in windows)
+        if not near_edge:
+            assert t == (ok[0] if ok else -1), (bnd, t)
     assert r < 6e-3
 
 
@@ -528,8 +536,10 @@ def test_attention_polynomial_kernel_tier_mixed(ops):
     qkv[1, 777, :hd] *= 600.0               # one query row of head 0, image 1
     pre, ref = _prescaled(qkv, heads, dtype=torch.float16)
     b = _logit_bound(pre, heads)
-    assert (b <= 2.0).sum() == 2 * heads - 2 and 2.0 < b[0, 3] < 11.0 and b[1, 0] > 60.0
-    out = ops.attention_prescaled(pre.cuda(), heads).float().cpu()
+    assert (b <= 2.0).sum() == 2 * heads - 2 and 3.6 < b[0, 3] < 11.0 and b[1, 0] > 60.0
+    out, tiers = ops.attention_prescaled(pre.cuda(), heads, return_tiers=True)
+    out, tiers = out.float().cpu(), tiers.cpu()
+    assert tiers[1, 0] == -1 and tiers[0, 3] == -1 and (tiers >= 0).sum() == 2 * heads - 2   # bound ~5 is beyond the largest window (3.5) too
     want = _attn_ref(ref, heads)
     assert torch.isfinite(out).all()
     assert rel(out, want) < 6e-3
