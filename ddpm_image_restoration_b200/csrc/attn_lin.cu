@@ -101,8 +101,9 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 
 template <int HD>
 __global__ void __launch_bounds__(256)
-attn_lin_moments_kernel(const __half* __restrict__ qkv, float* __restrict__ mom, int L, int C, int rows_per_slice) {
+attn_lin_moments_kernel(const __half* __restrict__ qkv, float* __restrict__ mom, int* __restrict__ counts, int L, int C, int rows_per_slice) {
     const int b = blockIdx.z, h = blockIdx.y, slice = blockIdx.x, H = gridDim.y;
+    if (b == 0 && h == 0 && slice == 0 && threadIdx.x <= MAXDEG) counts[threadIdx.x] = 0;      // per-degree work lists, filled by the decide kernel
     const long long rstride = 3LL * C;
     const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
     const int r0 = slice * rows_per_slice, r1 = min(L, r0 + rows_per_slice);
@@ -208,7 +209,7 @@ attn_lin_maxima_kernel(const __half* __restrict__ qkv, const float* __restrict__
 // (= sqrt(bound)) and every monomial of either side stays below sqrt(bound)^degree -- binary16-safe in the tensor-core kernels.
 __global__ void __launch_bounds__(128)
 attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ params, float* __restrict__ kmax, int* __restrict__ tier,
-                       int* __restrict__ zero_me, int n_bh, int slices, int hd, int max_set) {
+                       int* __restrict__ counts, int* __restrict__ lists, int* __restrict__ zero_me, int n_bh, int slices, int hd, int max_set) {
     const int bh = blockIdx.x * 128 + threadIdx.x;
     if (zero_me && bh == 0) *zero_me = 0;
     if (bh >= n_bh) return;
@@ -225,6 +226,10 @@ attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ params,
         for (int s = NSETS - 1; s >= 0; --s) if (s <= max_set && bound <= set_bound(s)) t = s;
     }
     tier[bh] = t;
+    if (t >= 0) {           // (image, head) pairs of one degree, in no particular order: each is computed independently
+        const int deg = set_degree(t);
+        lists[deg * n_bh + atomicAdd(&counts[deg], 1)] = bh;
+    }
     float* p = params + (long long)bh * PSTRIDE;
     if (t >= 0 && nq > 1e-20f && nk > 1e-20f) {
         const float g = sqrtf(nk / nq);
@@ -505,7 +510,7 @@ constexpr int simt_max_set(int hd) { return hd == 8 ? 3 : 1; }
 constexpr int tc_max_set(int hd) { return hd == 8 ? 5 : 3; }
 
 struct LinWs {              // carved out of the caller's workspace
-    int* tier; float* params; float* mom; float* mx; float* S; float* spart; void* tc;
+    int* tier; int* counts; int* lists; float* params; float* mom; float* mx; float* S; float* spart; void* tc;
     size_t bytes;
 };
 LinWs carve(void* base, int B, int L, int C, int heads, int hd) {
@@ -515,6 +520,8 @@ LinWs carve(void* base, int B, int L, int C, int heads, int hd) {
     char* p = (char*)base;
     auto take = [&](size_t n_bytes) { char* r = p; p += (n_bytes + 255) / 256 * 256; return r; };
     w.tier = (int*)take(bh * 4);
+    w.counts = (int*)take((MAXDEG + 1) * 4);
+    w.lists = (int*)take((MAXDEG + 1) * bh * 4);
     w.params = (float*)take(bh * PSTRIDE * 4);
     w.mom = (float*)take(bh * splits * 4 * hd * 4);
     w.mx = (float*)take(bh * splits * 4 * 4);
@@ -551,11 +558,11 @@ int launch_degree(const __half* qkv, const LinWs& w, bf16* out, int* flags, int 
 template <int HD>
 int prepass(const __half* qkv, const LinWs& w, float* kmax, int* declined, int B, int L, int C, int heads, int max_set, cudaStream_t st) {
     const int slices = lin_splits(B, L, heads), rps = ceil_div(L, slices);
-    attn_lin_moments_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, L, C, rps);
+    attn_lin_moments_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, w.counts, L, C, rps);
     DDPMIR_LAUNCH_CHECK();
     attn_lin_maxima_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, w.params, w.mx, L, C, rps);
     DDPMIR_LAUNCH_CHECK();
-    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, w.params, kmax, w.tier, declined, B * heads, slices, HD, max_set);
+    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, w.params, kmax, w.tier, w.counts, w.lists, declined, B * heads, slices, HD, max_set);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -584,7 +591,7 @@ int ddpmir_attention_lin(const void* qkv, void* out, float* kmax, int* flags, in
     if (rc != DDPMIR_OK) return rc;
     *tier_out = w.tier;
     if (max_set < 0) return DDPMIR_OK;
-    if (!simt) return ddpmir_attention_lin_tc(qkv, out, w.tier, w.params, w.tc, flags, B, L, C, heads, max_set, st);
+    if (!simt) return ddpmir_attention_lin_tc(qkv, out, w.tier, w.counts, w.lists, w.params, w.tc, flags, B, L, C, heads, max_set, st);
 #define LD(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_degree<HD, DEG>(q, w, (bf16*)out, flags, B, L, C, heads, st)
     if (hd == 8) { LD(8, 3); LD(8, 4); }
     else { LD(16, 3); }

@@ -44,5 +44,6 @@ __host__ __device__ constexpr int nfeat(int n, int deg) { return deg < 0 ? 0 : (
 
 // attn_lin_tc.cu
 size_t ddpmir_attention_lin_tc_workspace(int B, int L, int hd, int heads);
-int ddpmir_attention_lin_tc(const void* qkv, void* out, const int* tier, const float* params, void* ws, int* flags, int B, int L, int C,
-                            int heads, int max_set, cudaStream_t st);
+// counts [MAXDEG + 1], lists [MAXDEG + 1][B*heads]: the (image, head) pairs of every degree, compacted by the pre-pass
+int ddpmir_attention_lin_tc(const void* qkv, void* out, const int* tier, const int* counts, const int* lists, const float* params, void* ws,
+                            int* flags, int B, int L, int C, int heads, int max_set, cudaStream_t st);

@@ -32,6 +32,7 @@ struct Groups {
     int d1lo[MAXG], d1hi[MAXG];            // first-variable range of the group
     int chunks[MAXG];                      // 128-feature chunks of the group
     int base[MAXG];                        // first chunk of the group in the global feature order
+    int pad[MAXG];                         // zero octets that fill the group's last chunk
     int total;                             // chunks of all groups
 };
 
@@ -47,6 +48,7 @@ template <int HD, int DEG> struct Lay {
         Groups g{};
         if (FULL) {
             g.n = 1; g.d1lo[0] = 0; g.d1hi[0] = HD; g.chunks[0] = ((F + 7) / 8 + CH_OCT - 1) / CH_OCT; g.base[0] = 0;
+            g.pad[0] = g.chunks[0] * CH_OCT - (F + 7) / 8;
             g.total = g.chunks[0];
             return g;
         }
@@ -56,6 +58,7 @@ template <int HD, int DEG> struct Lay {
             int oct = g.n == 0 ? HDR : 0, lo = d1;
             while (d1 < HD && (oct + sub(d1) + CH_OCT - 1) / CH_OCT <= MAXCH) { oct += sub(d1); ++d1; }
             g.d1lo[g.n] = lo; g.d1hi[g.n] = d1; g.chunks[g.n] = (oct + CH_OCT - 1) / CH_OCT; g.base[g.n] = base;
+            g.pad[g.n] = g.chunks[g.n] * CH_OCT - oct;
             base += g.chunks[g.n]; ++g.n;
         }
         g.total = base;
@@ -142,36 +145,93 @@ __device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
+// %laneid / %tid.x through volatile asm: the compiler treats special-register reads as free to rematerialise and re-reads them (S2R,
+// ~25 cycles on a slow pipe) at every use inside the unrolled feature walk; an opaque value stays in its register
+__device__ __forceinline__ int opaque_lane() { int v; asm volatile("mov.u32 %0, %%laneid;" : "=r"(v)); return v; }
+__device__ __forceinline__ int opaque_tid() { int v; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(v)); return v; }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
 }
 
-// chunk boundary of the state kernel: this warp's 128 features x 32 keys are in shared memory -> the elected lane multiplies them
-// into the accumulators (two K = 16 MMAs), commits to the buffer's barrier, and the warp waits until the OTHER buffer (the one
-// it fills next) has been read by the MMAs issued from it two chunks ago.
-template <int NB>
-__device__ __noinline__ void state_publish(unsigned char* chunk, uint32_t vaddr, uint32_t tmem_d, uint64_t* bar_this, uint64_t* bar_next,
-                                           int uses_next, int lane) {
+// ---- chunk boundaries, out of line -------------------------------------------------------------------------------------------------
+// The unrolled feature walk is thousands of instructions long; whatever is inlined at each of its ~100 octet sites is paid for
+// in instruction-cache misses (measured: 3.5 stall cycles per issued instruction with the boundary work inlined).  So an octet
+// site is: pack, one 16-byte store through a 32-bit address, add, compare, predicated call.  Everything a boundary needs lives
+// in a small per-warp context in shared memory; the non-inlined boundary function gets its address and returns the address of
+// the next octet.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 q, c, 0x400000;\n\t"
+        "@!q trap;\n\t"
+        "nanosleep.u32 20;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t"
+        "}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+
+// state kernel, per-warp context (8 words): chunk buffers | barriers | accumulator base | value tile | n | c
+//   n = chunks published so far (whole kernel): chunk n lives in buffer n % NBUF;  c = chunks published for the current key tile
+constexpr int SC_CHUNK0 = 0, SC_BAR = 4, SC_TMEM = 8, SC_VADDR = 12, SC_N = 16, SC_C = 20, SC_BYTES = 32;
+// This warp's 128 features x 32 keys are in shared memory: the elected lane multiplies them into the accumulators (two K = 16
+// MMAs) and commits to the buffer's barrier; then the warp waits until the buffer it fills next has been read.
+template <int NB, int NBUF, int CHUNK_BYTES>
+__device__ __noinline__ uint32_t state_boundary(uint32_t ctx, int lane) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t chunk0 = lds32(ctx + SC_CHUNK0), bar = lds32(ctx + SC_BAR);
+    const int n = (int)lds32(ctx + SC_N);
+    const int buf = n % NBUF, nxt = (n + 1) % NBUF;
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        const uint32_t a0 = smem_u32(chunk);
+        const uint32_t a0 = chunk0 + buf * CHUNK_BYTES, vaddr = lds32(ctx + SC_VADDR);
+        const int c = (int)lds32(ctx + SC_C);
+        const uint32_t d = lds32(ctx + SC_TMEM) + (uint32_t)(c * NB);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-            umma_bf16(tmem_d, make_desc_noswz(a0 + ks * 256, 128, 512), make_desc_noswz(vaddr + ks * 256, 128, 512), IDESC, 1u);
-        umma_commit(bar_this);
+            umma_bf16(d, make_desc_noswz(a0 + ks * 256, 128, 512), make_desc_noswz(vaddr + ks * 256, 128, 512), IDESC, 1u);
+        umma_commit_addr(bar + buf * 8);
+        sts32(ctx + SC_N, (uint32_t)(n + 1));
+        sts32(ctx + SC_C, (uint32_t)(c + 1));
     }
     __syncwarp();
-    if (uses_next > 0) mbar_wait_warp<0>(bar_next, (uses_next - 1) & 1);
+    // chunk n + 1 reuses the buffer of chunk n + 1 - NBUF: wait for that chunk's commit (the ((n + 1) / NBUF)-th use of the buffer)
+    if (n + 1 >= NBUF) mbar_wait_addr(bar + nxt * 8, (uint32_t)((((n + 1) / NBUF) - 1) & 1));
+    return chunk0 + nxt * CHUNK_BYTES + lane * 16;
 }
-// chunk boundary of the output kernel: the thread's 128 features are in its TMEM lane -> arrive on the chunk's barrier, then wait
-// until the MMAs of chunk n - 2 have read the buffer that is filled next.  n = chunks published before this one.
-__device__ __noinline__ void out_publish(uint64_t* full_this, uint64_t* free_next, int n) {
+
+// output kernel, per-warp context: full barriers | free barriers | lane-quadrant TMEM base | n (chunks published so far)
+constexpr int OC_FULL = 0, OC_FREE = 4, OC_TADDR0 = 8, OC_N = 12, OC_BYTES = 16;
+// The thread's 128 features are in its TMEM lane: arrive on the chunk's barrier, then wait until the MMAs of chunk n - 1 have read
+// the buffer that is filled next.  Returns the TMEM address of the next octet.
+__device__ __noinline__ uint32_t out_boundary(uint32_t ctx, int lane) {
+    const int n = (int)lds32(ctx + OC_N);
+    const uint32_t full = lds32(ctx + OC_FULL), freeb = lds32(ctx + OC_FREE);
     tmem_wait_st();
     tc_fence_before();
-    mbar_arrive(full_this);
-    if (n >= 1) mbar_wait_warp<0>(free_next, ((n - 1) >> 1) & 1);
+    mbar_arrive_addr(full + (n & 1) * 8);
+    __syncwarp();
+    if (lane == 0) sts32(ctx + OC_N, (uint32_t)(n + 1));
+    __syncwarp();
+    if (n >= 1) mbar_wait_addr(freeb + ((n + 1) & 1) * 8, (uint32_t)(((n - 1) >> 1) & 1));
+    return lds32(ctx + OC_TADDR0) + ((n + 1) & 1) * 64;
 }
 
 // ---- coefficient table: n!/a! and degree of every (padded) feature, in the generator's order -------------------------------------
@@ -210,8 +270,11 @@ template <int HD, int DEG> struct StateTc {
     static constexpr int CHUNK_BYTES = CH_OCT * 32 * 16;             // [16 feature octets][32 keys][16 B]
     static constexpr int V_BYTES = NBO * 32 * 16;                    // [value octets][32 keys][16 B]
     static constexpr int XS_BYTES = L_::FULL ? 0 : 32 * HD * 4;
-    static constexpr int WARP_BYTES = 2 * CHUNK_BYTES + 2 * V_BYTES + XS_BYTES;
-    static constexpr int SMEM = 4 * WARP_BYTES + 128 + 128;
+    // chunk buffers per warp: two when several CTAs share the SM (their warps hide the latency between an MMA and its commit),
+    // four when the accumulators take all of TMEM and the SM holds a single CTA of four warps
+    static constexpr int NBUF = L_::maxchunks() * NB > 256 ? 4 : 2;
+    static constexpr int WARP_BYTES = NBUF * CHUNK_BYTES + 2 * V_BYTES + XS_BYTES;
+    static constexpr int SMEM = 4 * WARP_BYTES + 4 * SC_BYTES + 256 + 128;
     static constexpr int tmem_cols() { int c = L_::maxchunks() * NB, p = 32; while (p < c) p *= 2; return p; }
 };
 
@@ -226,17 +289,18 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
     if (set < 0 || set_degree(set) != DEG) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = opaque_tid(), lane = opaque_lane();
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     unsigned char* wbase = smem + warp * T::WARP_BYTES;
     unsigned char* chunk0 = wbase;                                   // 2 chunk buffers
-    unsigned char* vbuf0 = wbase + 2 * T::CHUNK_BYTES;               // 2 value buffers (key tile parity)
+    unsigned char* vbuf0 = wbase + T::NBUF * T::CHUNK_BYTES;         // 2 value buffers (key tile parity)
     float* xs = reinterpret_cast<float*>(vbuf0 + 2 * T::V_BYTES);    // !FULL: this warp's scaled keys for runtime-indexed reads
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * T::WARP_BYTES);      // [4 warps][2 buffers]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * T::WARP_BYTES);      // [4 warps][NBUF buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * T::NBUF);
+    const uint32_t ctx = smem_u32(tmem_slot + 4) + warp * SC_BYTES;            // this warp's boundary context
 
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 4 * T::NBUF; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
@@ -260,31 +324,30 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
     const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
     const int j0 = split * keys_per_split, j1 = min(L, j0 + keys_per_split);
     const float* par = params + (long long)(b * H + h) * PSTRIDE;
-    uint64_t* my_bar = bars + warp * 2;
+    uint64_t* my_bar = bars + warp * T::NBUF;
 
-    // (the chunk-boundary work is a separate, non-inlined function: inlined at every octet it pushes the unrolled feature walk
-    //  over the compiler's full-unroll size limit, and the walk then falls back to runtime loops over register arrays)
+    if (lane == 0) {
+        sts32(ctx + SC_CHUNK0, smem_u32(chunk0)); sts32(ctx + SC_BAR, smem_u32(my_bar)); sts32(ctx + SC_TMEM, tmem_base);
+        sts32(ctx + SC_N, 0u); sts32(ctx + SC_C, 0u);
+    }
+    __syncwarp();
     struct Sink {
-        unsigned char* chunk0; uint64_t* bar; uint32_t tmem_base, vaddr; int lane, oct, buf, uses0, uses1, nch_oct;
+        uint32_t wptr, wend, ctx; int lane, pad;        // where the next octet goes / end of the chunk being filled
         __device__ __forceinline__ void octet(const float (&v)[8], const int (&)[8]) {
-            *reinterpret_cast<uint4*>(chunk0 + buf * StateTc<HD, DEG>::CHUNK_BYTES + (oct & (CH_OCT - 1)) * 512 + lane * 16) = pack_octet(v);
-            ++oct;
-            if ((oct & (CH_OCT - 1)) == 0) {
-                const int uses = buf == 0 ? ++uses0 : ++uses1;
-                (void)uses;
-                const int nb = buf ^ 1;
-                state_publish<NB>(chunk0 + buf * StateTc<HD, DEG>::CHUNK_BYTES, vaddr, tmem_base + (uint32_t)((oct / CH_OCT - 1) * NB), &bar[buf], &bar[nb],
-                                  nb == 0 ? uses0 : uses1, lane);
-                buf = nb;
+            sts128(wptr, pack_octet(v));
+            wptr += 512;
+            if (wptr == wend) {
+                wptr = state_boundary<NB, StateTc<HD, DEG>::NBUF, StateTc<HD, DEG>::CHUNK_BYTES>(ctx, lane);
+                wend = wptr + CH_OCT * 512;
             }
         }
         __device__ __forceinline__ void finish() {
             const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int dummy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
-            while (oct < nch_oct) octet(z, dummy);
+            for (int i = 0; i < pad; ++i) octet(z, dummy);
         }
-    } sink{chunk0, my_bar, tmem_base, 0u, lane, 0, 0, 0, 0, nch * CH_OCT};
+    } sink{0u, 0u, ctx, lane, gi.pad[g]};
 
     uint4 kraw[HD / 8], vraw[HD / 8];
     auto fetch = [&](int jt) {
@@ -330,15 +393,22 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
 #pragma unroll
                 for (int d = 0; d < HD; ++d) xs[lane * HD + d] = x[d];
             }
-            sink.vaddr = smem_u32(vb);
+            if (lane == 0) { sts32(ctx + SC_VADDR, smem_u32(vb)); sts32(ctx + SC_C, 0u); }
+            __syncwarp();
         }
         fetch(jt + 128);
-        sink.oct = 0;
+        sink.wptr = smem_u32(chunk0) + ((int)lds32(ctx + SC_N) % T::NBUF) * T::CHUNK_BYTES + lane * 16;
+        sink.wend = sink.wptr + CH_OCT * 512;
         generate<HD, DEG, false>(x, [&](int d) { return xs[lane * HD + d]; }, gi.d1lo[g], gi.d1hi[g], g == 0, sink);
     }
-    // drain: the last MMAs of both buffers
-    if (sink.uses0 > 0) mbar_wait_warp<0>(&my_bar[0], (sink.uses0 - 1) & 1);
-    if (sink.uses1 > 0) mbar_wait_warp<0>(&my_bar[1], (sink.uses1 - 1) & 1);
+    // drain: the last commit of every buffer
+    {
+        const int n = (int)lds32(ctx + SC_N);
+        for (int i = 0; i < T::NBUF; ++i) {
+            const int last = n - 1 - i;                 // chunk numbers n-1, n-2, ... cover all buffers
+            if (last >= 0) mbar_wait_warp<0>(&my_bar[last % T::NBUF], (last / T::NBUF) & 1);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -389,19 +459,24 @@ template <int HD, int DEG> struct OutTc {
     static constexpr int NB = L_::NB;
     static constexpr int ST_BYTES = L_::maxchunks() * 128 * NB * 2;
     static constexpr int QS_BYTES = L_::FULL ? 0 : 128 * HD * 4;
-    static constexpr int SMEM = ST_BYTES + QS_BYTES + 128 + 128;
+    static constexpr int SMEM = ST_BYTES + QS_BYTES + 4 * OC_BYTES + 128 + 128;
     static constexpr int TCOLS = 256;                                 // 2 x 64 (feature chunks) + NB accumulator columns
 };
 
+// Persistent: the grid is a fixed two CTAs per SM; every CTA walks the work items (an (image, head) of this degree from the
+// pre-pass's list x a 128-row tile) with stride gridDim.x.  A degree nobody uses costs a few hundred CTAs that leave at once,
+// not a CTA per tile of the whole batch.
 template <int HD, int DEG>
 __global__ void __launch_bounds__(160, 2)      // 256 TMEM columns per CTA: two CTAs per SM
-attn_lin_out_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ tier, const float* __restrict__ params,
-                       const __half* __restrict__ ST, bf16* __restrict__ out, int* __restrict__ flags, int L, int C, Groups gi) {
+attn_lin_out_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ counts, const int* __restrict__ lists, int n_bh_total,
+                       const float* __restrict__ params, const __half* __restrict__ ST, bf16* __restrict__ out, int* __restrict__ flags,
+                       int L, int C, int H, Groups gi) {
     using T = OutTc<HD, DEG>;
     constexpr int NB = T::NB, TCOLS = T::TCOLS;
-    const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
-    const int set = tier[b * H + h];
-    if (set < 0 || set_degree(set) != DEG) return;
+    const int tiles = L / 128;
+    const long long n_items = (long long)counts[DEG] * tiles;
+    if ((long long)blockIdx.x >= n_items) return;
+    const int* list = lists + (long long)DEG * n_bh_total;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     unsigned char* sT = smem;
@@ -410,14 +485,14 @@ attn_lin_out_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ t
     uint64_t* freeb = full + 2;                                        // [2]
     uint64_t* gdone = freeb + 2;                                       // [1] all MMAs of a group have retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gdone + 1);
-    const int tid = threadIdx.x;
+    const uint32_t ctx0 = smem_u32(tmem_slot + 4);                     // [4 generator warps] boundary contexts
+    const int tid = opaque_tid();
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
         mbar_init(&full[0], 128); mbar_init(&full[1], 128);
         mbar_init(&freeb[0], 1); mbar_init(&freeb[1], 1);
         mbar_init(gdone, 1);
         fence_barrier_init();
-        flags[((long long)(b * H + h)) * (L / 128) + blockIdx.x] = 0;      // the quadratic tiers skip this tile
     }
     if (warp == 4) tmem_alloc(tmem_slot, TCOLS);
     tc_fence_before();
@@ -425,100 +500,113 @@ attn_lin_out_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ t
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_d = tmem_base + 128;
-    const float* par = params + (long long)(b * H + h) * PSTRIDE;
     const long long FPAD = (long long)gi.total * 128;
-    const __half* STg = ST + (long long)(b * H + h) * (FPAD * NB);
-    const int row = blockIdx.x * 128 + tid;
 
-    float x[HD];
-    if (warp < 4) {
-        const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((long long)b * L + row) * (3LL * C) + (long long)h * HD);
-#pragma unroll
-        for (int c = 0; c < HD / 8; ++c) unpack8h(__ldg(qp + c), &x[c * 8]);
-#pragma unroll
-        for (int d = 0; d < HD; ++d) {
-            x[d] = (x[d] - par[P_A + d]) * par[P_D + d];
-            if constexpr (!Lay<HD, DEG>::FULL) qs[d * 128 + tid] = x[d];
-        }
+    const int lane = opaque_lane();
+    const uint32_t ctx = ctx0 + (warp & 3) * OC_BYTES;
+    if (warp < 4 && lane == 0) {
+        sts32(ctx + OC_FULL, smem_u32(full)); sts32(ctx + OC_FREE, smem_u32(freeb));
+        sts32(ctx + OC_TADDR0, tmem_base + ((uint32_t)(warp * 32) << 16)); sts32(ctx + OC_N, 0u);
     }
+    __syncwarp();
     struct Sink {
-        uint64_t* full; uint64_t* freeb; uint32_t taddr0; int oct, buf, n;      // n: chunks published so far (all groups)
+        uint32_t taddr, ctx; int lane, pad;     // where the next octet goes (4 columns each; a chunk buffer = 64 columns, aligned)
         __device__ __forceinline__ void octet(const float (&v)[8], const int (&)[8]) {
-            tmem_st4(taddr0 + buf * 64 + (oct & (CH_OCT - 1)) * 4, pack_octet(v));
-            ++oct;
-            if ((oct & (CH_OCT - 1)) == 0) {
-                out_publish(&full[buf], &freeb[buf ^ 1], n);       // chunk n is complete; chunk n + 1 goes to the other buffer
-                ++n;
-                buf ^= 1;
-            }
+            tmem_st4(taddr, pack_octet(v));
+            taddr += 4;
+            if ((taddr & 63u) == 0u) taddr = out_boundary(ctx, lane);
         }
-        int end_oct;
         __device__ __forceinline__ void finish() {
             const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int dummy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
-            while (oct < end_oct) octet(z, dummy);
+            for (int i = 0; i < pad; ++i) octet(z, dummy);
         }
-    } sink{full, freeb, tmem_base + ((uint32_t)((warp & 3) * 32) << 16), 0, 0, 0, 0};
+    } sink{0u, ctx, lane, 0};
 
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int n_issued = 0;
-    for (int g = 0; g < gi.n; ++g) {
-        // the previous group's MMAs have read S^T: load this group's slice (generic proxy -> fence -> async proxy)
-        if (g > 0) mbar_wait(gdone, (g - 1) & 1);
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(STg + (long long)gi.base[g] * 128 * NB);
-            uint4* dst = reinterpret_cast<uint4*>(sT);
-            const int n16 = gi.chunks[g] * 128 * NB * 2 / 16;
-            for (int i = tid; i < n16; i += 160) dst[i] = __ldg(src + i);
-        }
-        fence_proxy_async();
-        __syncthreads();
+    int n_issued = 0;          // issuer warp: chunks multiplied so far
+    int gcount = 0;            // groups completed so far (every thread counts them the same way)
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int bh = list[item / tiles], tile = (int)(item % tiles);
+        const int b = bh / H, h = bh % H;
+        const float* par = params + (long long)bh * PSTRIDE;
+        const __half* STg = ST + (long long)bh * (FPAD * NB);
+        const int row = tile * 128 + tid;
+        if (tid == 0) flags[(long long)bh * tiles + tile] = 0;          // the quadratic tiers skip this tile
+        float x[HD];
         if (warp < 4) {
-            sink.oct = 0;
-            sink.end_oct = gi.chunks[g] * CH_OCT;
-            generate<HD, DEG, false>(x, [&](int d) { return qs[d * 128 + tid]; }, gi.d1lo[g], gi.d1hi[g], g == 0, sink);
-        } else {
-            const bool leader = elect_one();
-            const uint32_t s0 = smem_u32(sT);
-            for (int c = 0; c < gi.chunks[g]; ++c, ++n_issued) {
-                const int buf = n_issued & 1;
-                mbar_wait_warp<0>(&full[buf], (n_issued >> 1) & 1);
-                tc_fence_after();
-                if (leader) {
+            const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((long long)b * L + row) * (3LL * C) + (long long)h * HD);
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_bf16_ts(tmem_d, tmem_base + buf * 64 + ks * 8,
-                                     make_desc_noswz(s0 + (uint32_t)((c * 16 + ks * 2) * (NB / 8) * 128), (NB / 8) * 128, 128), IDESC,
-                                     (n_issued > 0 || ks > 0) ? 1u : 0u);
-                    umma_commit(&freeb[buf]);
-                    if (c == gi.chunks[g] - 1) umma_commit(gdone);
-                }
-                __syncwarp();
+            for (int c = 0; c < HD / 8; ++c) unpack8h(__ldg(qp + c), &x[c * 8]);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) {
+                x[d] = (x[d] - par[P_A + d]) * par[P_D + d];
+                if constexpr (!Lay<HD, DEG>::FULL) qs[d * 128 + tid] = x[d];
             }
         }
-    }
-    if (warp < 4) {
-        mbar_wait(gdone, (gi.n - 1) & 1);
+        bool first_mma = true;
+        for (int g = 0; g < gi.n; ++g, ++gcount) {
+            // the previous group's MMAs have read S^T: load this group's slice (generic proxy -> fence -> async proxy)
+            if (gcount > 0) mbar_wait(gdone, (gcount - 1) & 1);
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(STg + (long long)gi.base[g] * 128 * NB);
+                uint4* dst = reinterpret_cast<uint4*>(sT);
+                const int n16 = gi.chunks[g] * 128 * NB * 2 / 16;
+                for (int i = tid; i < n16; i += 160) dst[i] = __ldg(src + i);
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (warp < 4) {
+                sink.pad = gi.pad[g];
+                sink.taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ((int)lds32(ctx + OC_N) & 1) * 64;
+                generate<HD, DEG, false>(x, [&](int d) { return qs[d * 128 + tid]; }, gi.d1lo[g], gi.d1hi[g], g == 0, sink);
+            } else {
+                const bool leader = elect_one();
+                const uint32_t s0 = smem_u32(sT);
+                for (int c = 0; c < gi.chunks[g]; ++c, ++n_issued) {
+                    const int buf = n_issued & 1;
+                    mbar_wait_warp<0>(&full[buf], (n_issued >> 1) & 1);
+                    tc_fence_after();
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_bf16_ts(tmem_d, tmem_base + buf * 64 + ks * 8,
+                                         make_desc_noswz(s0 + (uint32_t)((c * 16 + ks * 2) * (NB / 8) * 128), (NB / 8) * 128, 128), IDESC,
+                                         (first_mma && ks == 0) ? 0u : 1u);
+                        umma_commit(&freeb[buf]);
+                        if (c == gi.chunks[g] - 1) umma_commit(gdone);
+                    }
+                    first_mma = false;
+                    __syncwarp();
+                }
+            }
+        }
+        if (warp < 4) {
+            mbar_wait(gdone, (gcount - 1) & 1);
+            tc_fence_after();
+            float o[NB];
+#pragma unroll
+            for (int q = 0; q < NB / 16; ++q) {
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + q * 16, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[q * 16 + i] = v[i];
+            }
+            const float inv = 1.f / o[HD];
+            bf16* op = out + ((long long)b * L + row) * C + (long long)h * HD;
+#pragma unroll
+            for (int c8 = 0; c8 < HD / 8; ++c8) {
+                uint4 w;
+                __nv_bfloat162* wp = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wp[i] = __floats2bfloat162_rn(o[c8 * 8 + 2 * i] * inv, o[c8 * 8 + 2 * i + 1] * inv);
+                *reinterpret_cast<uint4*>(op + c8 * 8) = w;
+            }
+            tc_fence_before();
+        }
+        __syncthreads();            // the accumulator has been read: the next item's first MMA may overwrite it
         tc_fence_after();
-        float o[NB];
-#pragma unroll
-        for (int q = 0; q < NB / 16; ++q) {
-            float v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + q * 16, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[q * 16 + i] = v[i];
-        }
-        const float inv = 1.f / o[HD];
-        bf16* op = out + ((long long)b * L + row) * C + (long long)h * HD;
-#pragma unroll
-        for (int c8 = 0; c8 < HD / 8; ++c8) {
-            uint4 w;
-            __nv_bfloat162* wp = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) wp[i] = __floats2bfloat162_rn(o[c8 * 8 + 2 * i] * inv, o[c8 * 8 + 2 * i + 1] * inv);
-            *reinterpret_cast<uint4*>(op + c8 * 8) = w;
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -537,8 +625,8 @@ template <int HD, int DEG> constexpr size_t tc_bytes_per_bh(int splits) {
 }
 
 template <int HD, int DEG>
-int launch_tc(const __half* qkv, const int* tier, const float* params, void* ws, bf16* out, int* flags, int B, int L, int C, int heads,
-              cudaStream_t st) {
+int launch_tc(const __half* qkv, const int* tier, const int* counts, const int* lists, const float* params, void* ws, bf16* out, int* flags,
+              int B, int L, int C, int heads, cudaStream_t st) {
     constexpr Groups gi = Lay<HD, DEG>::groups();
     constexpr int FP = gi.total * 128, NB = Lay<HD, DEG>::NB;
     const int splits = tc_splits(B, L, heads, gi.n);
@@ -558,7 +646,9 @@ int launch_tc(const __half* qkv, const int* tier, const float* params, void* ws,
     DDPMIR_LAUNCH_CHECK();
     attn_lin_reduce_tc_kernel<HD, DEG><<<dim3(gi.total, B * heads), 256, 0, st>>>(spart, tier, ST, splits, 1.f / (float)L, gi.total);
     DDPMIR_LAUNCH_CHECK();
-    attn_lin_out_tc_kernel<HD, DEG><<<dim3(L / 128, heads, B), 160, OutTc<HD, DEG>::SMEM, st>>>(qkv, tier, params, ST, out, flags, L, C, gi);
+    const long long items = (long long)B * heads * (L / 128);
+    const int grid = (int)(items < 2 * 148 ? items : 2 * 148);
+    attn_lin_out_tc_kernel<HD, DEG><<<grid, 160, OutTc<HD, DEG>::SMEM, st>>>(qkv, counts, lists, B * heads, params, ST, out, flags, L, C, heads, gi);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -580,13 +670,13 @@ size_t ddpmir_attention_lin_tc_workspace(int B, int L, int hd, int heads) {
     return m;
 }
 
-int ddpmir_attention_lin_tc(const void* qkv, void* out, const int* tier, const float* params, void* ws, int* flags, int B, int L, int C,
-                            int heads, int max_set, cudaStream_t st) {
+int ddpmir_attention_lin_tc(const void* qkv, void* out, const int* tier, const int* counts, const int* lists, const float* params, void* ws,
+                            int* flags, int B, int L, int C, int heads, int max_set, cudaStream_t st) {
     const int hd = C / heads;
     if ((hd != 8 && hd != 16) || L % 128 != 0) return DDPMIR_ERR_UNSUPPORTED;
     const __half* q = (const __half*)qkv;
     int rc = DDPMIR_OK;
-#define LT(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_tc<HD, DEG>(q, tier, params, ws, (bf16*)out, flags, B, L, C, heads, st)
+#define LT(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_tc<HD, DEG>(q, tier, counts, lists, params, ws, (bf16*)out, flags, B, L, C, heads, st)
     if (hd == 8) { LT(8, 3); LT(8, 4); LT(8, 5); LT(8, 6); }
     else { LT(16, 3); LT(16, 4); }
 #undef LT

@@ -17,6 +17,7 @@ if "ATTN_LIN" in os.environ:      # largest polynomial set of the polynomial-ker
     _lib.lib().ddpmir_attention_set_lin(int(os.environ["ATTN_LIN"]))
 attn = ops.attention_prescaled if pre else ops.attention
 C = hd * heads
+torch.manual_seed(0)
 scale = float(os.environ.get("ATTN_SCALE", "1.0"))   # 0.35: logit bound < 2, 0.8: < 11 (half-precision tiers), 1.0+: bf16 tier
 qkv = torch.randn(B, L, 3 * C, device="cuda") * scale
 if pre:
@@ -25,6 +26,9 @@ qkv = qkv.to(torch.float16 if os.environ.get("ATTN_F16", "1") == "1" and pre els
 for _ in range(2):
     out = attn(qkv, heads)
 torch.cuda.synchronize()
+if pre and qkv.dtype == torch.float16:
+    _, tiers = ops.attention_prescaled(qkv, heads, return_tiers=True)
+    print("polynomial sets (-1 = quadratic tiers):", dict(zip(*[t.tolist() for t in tiers.flatten().unique(return_counts=True)])))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n = 3
 e0.record()
