@@ -37,10 +37,17 @@ def host_threads():
 
 
 def _codec_thread_init():
-    """Codec threads (and the encoder workers they spawn, which inherit it) run at a lower scheduling priority than the thread
-    that launches the GPU kernels: with every core busy encoding, a starved launcher thread shows up as idle gaps on the GPU."""
+    """Codec threads (and the encoder workers they spawn, which inherit it) yield to the thread that launches the GPU kernels: with
+    every core busy encoding, a launcher thread that has to queue for a core shows up as idle gaps on the GPU.  SCHED_IDLE where
+    the kernel grants it (any normal-priority thread preempts at once), nice 10 otherwise."""
+    tid = threading.get_native_id()
     try:
-        os.setpriority(os.PRIO_PROCESS, threading.get_native_id(), 10)
+        os.sched_setscheduler(tid, os.SCHED_IDLE, os.sched_param(0))
+        return
+    except (OSError, AttributeError):
+        pass
+    try:
+        os.setpriority(os.PRIO_PROCESS, tid, 10)
     except (OSError, AttributeError):  # pragma: no cover
         pass
 

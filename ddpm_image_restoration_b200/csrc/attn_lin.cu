@@ -209,7 +209,8 @@ attn_lin_maxima_kernel(const __half* __restrict__ qkv, const float* __restrict__
 // (= sqrt(bound)) and every monomial of either side stays below sqrt(bound)^degree -- binary16-safe in the tensor-core kernels.
 __global__ void __launch_bounds__(128)
 attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ params, float* __restrict__ kmax, int* __restrict__ tier,
-                       int* __restrict__ counts, int* __restrict__ lists, int* __restrict__ zero_me, int n_bh, int slices, int hd, int max_set) {
+                       int* __restrict__ counts, int* __restrict__ lists, int* __restrict__ zero_me, int n_bh, int slices, int hd, int max_set,
+                       unsigned mask) {
     const int bh = blockIdx.x * 128 + threadIdx.x;
     if (zero_me && bh == 0) *zero_me = 0;
     if (bh >= n_bh) return;
@@ -223,7 +224,7 @@ attn_lin_decide_kernel(const float* __restrict__ mx, float* __restrict__ params,
     const float bound = nq * nk * 1.0001f;
     int t = -1;
     if (bound == bound && emax == emax && fabsf(emax) < 100.f) {           // NaN / absurd -> quadratic tiers (which hand it on to the exact kernel)
-        for (int s = NSETS - 1; s >= 0; --s) if (s <= max_set && bound <= set_bound(s)) t = s;
+        for (int s = NSETS - 1; s >= 0; --s) if (s <= max_set && ((mask >> s) & 1u) && bound <= set_bound(s)) t = s;
     }
     tier[bh] = t;
     if (t >= 0) {           // (image, head) pairs of one degree, in no particular order: each is computed independently
@@ -504,17 +505,16 @@ int lin_splits(int B, int L, int heads) {
     return s < 1 ? 1 : s;
 }
 
-// SIMT path: head_dim 8 up to degree 4 (set 3), head_dim 16 up to degree 3 (set 1): beyond that the fp32 accumulation costs more
-// than the quadratic tier.  Tensor-core path (attn_lin_tc.cu): head_dim 8 up to degree 6 (set 5), head_dim 16 up to degree 4 (set 3).
-constexpr int simt_max_set(int hd) { return hd == 8 ? 3 : 1; }
-constexpr int tc_max_set(int hd) { return hd == 8 ? 5 : 3; }
+// SIMT path: head_dim 8 up to degree 4, head_dim 16 up to degree 3: beyond that the fp32 accumulation costs more than the
+// quadratic tier.  Tensor-core path (attn_lin_tc.cu): head_dim 8 up to degree 6, head_dim 16 up to degree 4 (set_mask, attn_lin.cuh).
+constexpr int simt_max_degree(int hd) { return hd == 8 ? 4 : 3; }
 
 struct LinWs {              // carved out of the caller's workspace
     int* tier; int* counts; int* lists; float* params; float* mom; float* mx; float* S; float* spart; void* tc;
     size_t bytes;
 };
 LinWs carve(void* base, int B, int L, int C, int heads, int hd) {
-    const int F = nfeat(hd, set_degree(simt_max_set(hd))), NC = hd + 1, NCP = (NC + 3) / 4 * 4, splits = lin_splits(B, L, heads);
+    const int F = nfeat(hd, simt_max_degree(hd)), NC = hd + 1, NCP = (NC + 3) / 4 * 4, splits = lin_splits(B, L, heads);
     const size_t bh = (size_t)B * heads;
     LinWs w;
     char* p = (char*)base;
@@ -556,13 +556,14 @@ int launch_degree(const __half* qkv, const LinWs& w, bf16* out, int* flags, int 
 }
 
 template <int HD>
-int prepass(const __half* qkv, const LinWs& w, float* kmax, int* declined, int B, int L, int C, int heads, int max_set, cudaStream_t st) {
+int prepass(const __half* qkv, const LinWs& w, float* kmax, int* declined, int B, int L, int C, int heads, int max_set, unsigned mask,
+            cudaStream_t st) {
     const int slices = lin_splits(B, L, heads), rps = ceil_div(L, slices);
     attn_lin_moments_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, w.counts, L, C, rps);
     DDPMIR_LAUNCH_CHECK();
     attn_lin_maxima_kernel<HD><<<dim3(slices, heads, B), 256, 0, st>>>(qkv, w.mom, w.params, w.mx, L, C, rps);
     DDPMIR_LAUNCH_CHECK();
-    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, w.params, kmax, w.tier, w.counts, w.lists, declined, B * heads, slices, HD, max_set);
+    attn_lin_decide_kernel<<<ceil_div(B * heads, 128), 128, 0, st>>>(w.mx, w.params, kmax, w.tier, w.counts, w.lists, declined, B * heads, slices, HD, max_set, mask);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
@@ -585,14 +586,18 @@ int ddpmir_attention_lin(const void* qkv, void* out, float* kmax, int* flags, in
     if (hd != 8 && hd != 16) return DDPMIR_ERR_UNSUPPORTED;
     const LinWs w = carve(lin_ws, B, L, C, heads, hd);
     const __half* q = (const __half*)qkv;
-    const int cap = simt ? simt_max_set(hd) : tc_max_set(hd);
-    if (max_set > cap) max_set = cap;
-    int rc = hd == 8 ? prepass<8>(q, w, kmax, declined, B, L, C, heads, max_set, st) : prepass<16>(q, w, kmax, declined, B, L, C, heads, max_set, st);
+    const unsigned mask = set_mask(hd, L, simt != 0);
+    if (max_set >= NSETS) max_set = NSETS - 1;
+    int rc = hd == 8 ? prepass<8>(q, w, kmax, declined, B, L, C, heads, max_set, mask, st)
+                     : prepass<16>(q, w, kmax, declined, B, L, C, heads, max_set, mask, st);
     if (rc != DDPMIR_OK) return rc;
     *tier_out = w.tier;
     if (max_set < 0) return DDPMIR_OK;
-    if (!simt) return ddpmir_attention_lin_tc(qkv, out, w.tier, w.counts, w.lists, w.params, w.tc, flags, B, L, C, heads, max_set, st);
-#define LD(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_degree<HD, DEG>(q, w, (bf16*)out, flags, B, L, C, heads, st)
+    int top = -1;                                        // largest degree any (image, head) of this call can have been given
+    for (int s = 0; s <= max_set; ++s) if ((mask >> s) & 1u) top = set_degree(s);
+    if (top < 0) return DDPMIR_OK;
+    if (!simt) return ddpmir_attention_lin_tc(qkv, out, w.tier, w.counts, w.lists, w.params, w.tc, flags, B, L, C, heads, top, st);
+#define LD(HD, DEG) if (rc == DDPMIR_OK && top >= DEG) rc = launch_degree<HD, DEG>(q, w, (bf16*)out, flags, B, L, C, heads, st)
     if (hd == 8) { LD(8, 3); LD(8, 4); }
     else { LD(16, 3); }
 #undef LD

@@ -263,6 +263,19 @@ __global__ void attn_lin_table_kernel(Groups gi) {
     generate<HD, DEG, true>(x, [](int) { return 1.f; }, gi.d1lo[g], gi.d1hi[g], g == 0, sink);
 }
 
+// Key slices per (image, head): chosen ON THE DEVICE from how many (image, head) pairs the pre-pass gave this degree, so that a
+// handful of pairs still fills the machine (every thread of the state and reduce kernels derives the same number).
+constexpr int TC_ITEMS_TARGET = 592;
+__host__ __device__ inline int tc_splits_for(int count, int ngroups, int L) {
+    if (count <= 0) return 1;
+    int s = TC_ITEMS_TARGET / (count * ngroups);
+    const int cap = L / 2048 < 32 ? L / 2048 : 32;
+    if (s > cap) s = cap;
+    return s < 1 ? 1 : s;
+}
+// partial-sum slots a call can need: count * splits <= count + TC_ITEMS_TARGET / ngroups
+__host__ __device__ inline int tc_slots(int n_bh, int ngroups) { return n_bh + TC_ITEMS_TARGET / ngroups + 1; }
+
 // ---- S^T partial sums: features x keys on the tensor core ---------------------------------------------------------------------------
 template <int HD, int DEG> struct StateTc {
     using L_ = Lay<HD, DEG>;
@@ -278,15 +291,19 @@ template <int HD, int DEG> struct StateTc {
     static constexpr int tmem_cols() { int c = L_::maxchunks() * NB, p = 32; while (p < c) p *= 2; return p; }
 };
 
+// Persistent over the work items (list entry of this degree, feature group, key slice).
 template <int HD, int DEG>
 __global__ void __launch_bounds__(128)
-attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ tier, const float* __restrict__ params,
-                         float* __restrict__ spart, int L, int C, int keys_per_split, Groups gi) {
+attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ counts, const int* __restrict__ lists, int n_bh_total,
+                         const float* __restrict__ params, float* __restrict__ spart, int L, int C, int H, Groups gi) {
     using T = StateTc<HD, DEG>;
     constexpr int NB = T::NB, NBO = T::NBO, TCOLS = T::tmem_cols();
-    const int H = gridDim.y / gi.n, h = blockIdx.y / gi.n, g = blockIdx.y % gi.n, b = blockIdx.z, split = blockIdx.x;
-    const int set = tier[b * H + h];
-    if (set < 0 || set_degree(set) != DEG) return;
+    const int count = counts[DEG];
+    const int splits = tc_splits_for(count, gi.n, L);
+    const int n_items = count * gi.n * splits;
+    if ((int)blockIdx.x >= n_items) return;
+    const int* list = lists + (long long)DEG * n_bh_total;
+    const int keys_per_split = ((L + splits - 1) / splits + 127) / 128 * 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     const int tid = opaque_tid(), lane = opaque_lane();
@@ -308,22 +325,6 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nch = gi.chunks[g];
-    {   // clear this warp's lane quadrant of the accumulators
-        uint32_t z[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = 0u;
-        for (int c = 0; c < nch * NB / 16; ++c) tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 16, z);
-        tmem_wait_st();
-        tc_fence_before();
-    }
-    __syncthreads();
-    tc_fence_after();
-
-    const long long rstride = 3LL * C;
-    const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
-    const int j0 = split * keys_per_split, j1 = min(L, j0 + keys_per_split);
-    const float* par = params + (long long)(b * H + h) * PSTRIDE;
     uint64_t* my_bar = bars + warp * T::NBUF;
 
     if (lane == 0) {
@@ -347,7 +348,27 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
 #pragma unroll 1
             for (int i = 0; i < pad; ++i) octet(z, dummy);
         }
-    } sink{0u, 0u, ctx, lane, gi.pad[g]};
+    } sink{0u, 0u, ctx, lane, 0};
+
+    const long long rstride = 3LL * C;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int li = item / (gi.n * splits), g = (item / splits) % gi.n, split = item % splits;
+    const int bh = list[li], b = bh / H, h = bh % H;
+    const int nch = gi.chunks[g];
+    sink.pad = gi.pad[g];
+    {   // clear this warp's lane quadrant of the accumulators
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+        for (int c = 0; c < nch * NB / 16; ++c) tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 16, z);
+        tmem_wait_st();
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    const __half* base = qkv + (long long)b * L * rstride + (long long)h * HD;
+    const int j0 = split * keys_per_split, j1 = min(L, j0 + keys_per_split);
+    const float* par = params + (long long)bh * PSTRIDE;
 
     uint4 kraw[HD / 8], vraw[HD / 8];
     auto fetch = [&](int jt) {
@@ -414,7 +435,7 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
     tc_fence_after();
     // epilogue: thread = feature row of every chunk
     const int FPAD = gi.total * 128;
-    float* dst = spart + (((long long)(b * H + h)) * gridDim.x + split) * ((long long)FPAD * NB);
+    float* dst = spart + ((long long)li * splits + split) * ((long long)FPAD * NB);      // slot = (list position, slice)
     for (int c = 0; c < nch; ++c) {
         const int f = (gi.base[g] + c) * 128 + warp * 32 + lane;
 #pragma unroll
@@ -427,6 +448,10 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
         }
     }
     tc_fence_before();
+    __syncthreads();            // every warp has read its accumulators: the next item may clear them
+    tc_fence_after();
+    }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
@@ -434,14 +459,18 @@ attn_lin_state_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__
 // S^T (f16, K-major B operand: [feature octet][value octet][8 values][8 features]) = c_n n!/a! / L * sum over the key slices
 template <int HD, int DEG>
 __global__ void __launch_bounds__(256)
-attn_lin_reduce_tc_kernel(const float* __restrict__ spart, const int* __restrict__ tier, __half* __restrict__ ST, int splits, float inv_l,
-                          int total_chunks) {
+attn_lin_reduce_tc_kernel(const float* __restrict__ spart, const int* __restrict__ tier, const int* __restrict__ counts,
+                          const int* __restrict__ lists, int n_bh_total, __half* __restrict__ ST, int L, int ngroups, int total_chunks) {
     constexpr int NB = Lay<HD, DEG>::NB;
-    const int bh = blockIdx.y, chunk = blockIdx.x;
+    const int li = blockIdx.y, chunk = blockIdx.x;
+    const int count = counts[DEG];
+    if (li >= count) return;
+    const int splits = tc_splits_for(count, ngroups, L);
+    const int bh = lists[(long long)DEG * n_bh_total + li];
     const int set = tier[bh];
-    if (set < 0 || set_degree(set) != DEG) return;
+    const float inv_l = 1.f / (float)L;
     const long long FPAD = (long long)total_chunks * 128;
-    const float* src = spart + (long long)bh * splits * (FPAD * NB) + (long long)chunk * 128 * NB;
+    const float* src = spart + (long long)li * splits * (FPAD * NB) + (long long)chunk * 128 * NB;
     __half* dst = ST + (long long)bh * (FPAD * NB) + (long long)chunk * 128 * NB;
     for (int i = threadIdx.x; i < 128 * NB; i += 256) {
         const int fl = i / NB, col = i % NB, f = chunk * 128 + fl;
@@ -613,24 +642,11 @@ attn_lin_out_tc_kernel(const __half* __restrict__ qkv, const int* __restrict__ c
     if (warp == 4) tmem_dealloc(tmem_base, TCOLS);
 }
 
-int tc_splits(int B, int L, int heads, int ngroups) {
-    int s = 592 / (B * heads * ngroups);
-    const int cap = L / 2048;
-    if (s > cap) s = cap;
-    return s < 1 ? 1 : s;
-}
-template <int HD, int DEG> constexpr size_t tc_bytes_per_bh(int splits) {
-    constexpr int FP = Lay<HD, DEG>::groups().total * 128, NB = Lay<HD, DEG>::NB;
-    return (size_t)FP * NB * 2 + (size_t)splits * FP * NB * 4;
-}
-
 template <int HD, int DEG>
 int launch_tc(const __half* qkv, const int* tier, const int* counts, const int* lists, const float* params, void* ws, bf16* out, int* flags,
               int B, int L, int C, int heads, cudaStream_t st) {
     constexpr Groups gi = Lay<HD, DEG>::groups();
     constexpr int FP = gi.total * 128, NB = Lay<HD, DEG>::NB;
-    const int splits = tc_splits(B, L, heads, gi.n);
-    const int kps = (ceil_div(L, splits) + 127) / 128 * 128;
     __half* ST = (__half*)ws;
     float* spart = (float*)((char*)ws + ((size_t)B * heads * FP * NB * 2 + 255) / 256 * 256);
     static PerDevice ready;
@@ -642,9 +658,15 @@ int launch_tc(const __half* qkv, const int* tier, const int* counts, const int* 
         DDPMIR_LAUNCH_CHECK();
         done = 1;
     }
-    attn_lin_state_tc_kernel<HD, DEG><<<dim3(splits, heads * gi.n, B), 128, StateTc<HD, DEG>::SMEM, st>>>(qkv, tier, params, spart, L, C, kps, gi);
-    DDPMIR_LAUNCH_CHECK();
-    attn_lin_reduce_tc_kernel<HD, DEG><<<dim3(gi.total, B * heads), 256, 0, st>>>(spart, tier, ST, splits, 1.f / (float)L, gi.total);
+    {
+        // two to three CTAs per SM where TMEM and shared memory allow it, one where the accumulators take all 512 columns
+        const int per_sm = StateTc<HD, DEG>::tmem_cols() > 256 ? 1 : StateTc<HD, DEG>::tmem_cols() > 128 ? 2 : 3;
+        const int max_items = B * heads * gi.n * 32;
+        const int grid = max_items < per_sm * 148 ? max_items : per_sm * 148;
+        attn_lin_state_tc_kernel<HD, DEG><<<grid, 128, StateTc<HD, DEG>::SMEM, st>>>(qkv, counts, lists, B * heads, params, spart, L, C, heads, gi);
+        DDPMIR_LAUNCH_CHECK();
+    }
+    attn_lin_reduce_tc_kernel<HD, DEG><<<dim3(gi.total, B * heads), 256, 0, st>>>(spart, tier, counts, lists, B * heads, ST, L, gi.n, gi.total);
     DDPMIR_LAUNCH_CHECK();
     const long long items = (long long)B * heads * (L / 128);
     const int grid = (int)(items < 2 * 148 ? items : 2 * 148);
@@ -663,7 +685,7 @@ size_t ddpmir_attention_lin_tc_workspace(int B, int L, int hd, int heads) {
     };
     const size_t bh = (size_t)B * heads;
 #define SZ(HD, DEG) { constexpr Groups gi = Lay<HD, DEG>::groups(); constexpr size_t FP = (size_t)gi.total * 128, NB = Lay<HD, DEG>::NB; \
-                      upd(bh * FP * NB * 2, bh * tc_splits(B, L, heads, gi.n) * FP * NB * 4); }
+                      upd(bh * FP * NB * 2, (size_t)tc_slots((int)bh, gi.n) * FP * NB * 4); }
     if (hd == 8) { SZ(8, 3) SZ(8, 4) SZ(8, 5) SZ(8, 6) }
     else if (hd == 16) { SZ(16, 3) SZ(16, 4) }
 #undef SZ
@@ -671,12 +693,12 @@ size_t ddpmir_attention_lin_tc_workspace(int B, int L, int hd, int heads) {
 }
 
 int ddpmir_attention_lin_tc(const void* qkv, void* out, const int* tier, const int* counts, const int* lists, const float* params, void* ws,
-                            int* flags, int B, int L, int C, int heads, int max_set, cudaStream_t st) {
+                            int* flags, int B, int L, int C, int heads, int max_degree, cudaStream_t st) {
     const int hd = C / heads;
     if ((hd != 8 && hd != 16) || L % 128 != 0) return DDPMIR_ERR_UNSUPPORTED;
     const __half* q = (const __half*)qkv;
     int rc = DDPMIR_OK;
-#define LT(HD, DEG) if (rc == DDPMIR_OK && set_degree(max_set) >= DEG) rc = launch_tc<HD, DEG>(q, tier, counts, lists, params, ws, (bf16*)out, flags, B, L, C, heads, st)
+#define LT(HD, DEG) if (rc == DDPMIR_OK && max_degree >= DEG) rc = launch_tc<HD, DEG>(q, tier, counts, lists, params, ws, (bf16*)out, flags, B, L, C, heads, st)
     if (hd == 8) { LT(8, 3); LT(8, 4); LT(8, 5); LT(8, 6); }
     else { LT(16, 3); LT(16, 4); }
 #undef LT

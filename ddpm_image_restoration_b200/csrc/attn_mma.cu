@@ -643,7 +643,7 @@ int g_expmode = -1;   // -1 = auto: mode 3 (25 % of the exps on the FMA pipe) at
 int g_mt = 1;
 int g_poly = -1;      // bounded kernel: score tiles of 8 on the FMA pipe (-1 = auto), +8 = degree-2 instead of degree-3 polynomial
 int g_split16 = 0;    // half-precision tier (attn_tc16.cu): MUFU share of its two FMA-pipe variants, 0 = default
-int g_lin_max_set = 5; // polynomial-kernel tier (attn_lin.cu): largest polynomial set it may use, -1 = tier off
+int g_lin_max_set = 6; // polynomial-kernel tier (attn_lin.cu): largest polynomial set it may use, -1 = tier off
 int g_lin_simt = 0;    // ... 1 = its fp32 SIMT kernels instead of the tcgen05 ones
 
 }  // namespace
@@ -669,12 +669,12 @@ size_t ddpmir_attention_lin_workspace(int B, int L, int C, int heads);
 int ddpmir_attention_lin(const void* qkv, void* out, float* kmax, int* flags, int* declined, void* lin_ws, const int** tier_out,
                          int B, int L, int C, int heads, int max_set, int simt, cudaStream_t st);
 
-// test / tuning hook: largest polynomial set of the polynomial-kernel tier (0..5, see attn_lin.cuh), -1 switches the tier off;
+// test / tuning hook: largest polynomial set of the polynomial-kernel tier (0..6, see attn_lin.cuh), -1 switches the tier off;
 // +16 takes the tier's fp32 SIMT kernels instead of the tcgen05 ones
 extern "C" int ddpmir_attention_set_lin(int max_set) {
     if (max_set < 0) { g_lin_max_set = -1; g_lin_simt = 0; return DDPMIR_OK; }
     g_lin_simt = (max_set >> 4) & 1;
-    g_lin_max_set = (max_set & 15) > 5 ? 5 : (max_set & 15);
+    g_lin_max_set = (max_set & 15) > 6 ? 6 : (max_set & 15);
     return DDPMIR_OK;
 }
 

@@ -62,6 +62,10 @@ def spy(qkv, heads):
         b999 = nq.sort(dim=1).values[:, int(0.999 * L)] * nk.sort(dim=1).values[:, int(0.999 * L)]
         b99 = nq.sort(dim=1).values[:, int(0.99 * L)] * nk.sort(dim=1).values[:, int(0.99 * L)]
         print(f"      balanced bound {f(nq.amax(1) * nk.amax(1))} | without the top 0.1% rows+keys {f(b999)} | without the top 1% {f(b99)}")
+    if qkv.dtype == torch.float16:
+        out, tiers = orig(qkv, heads, return_tiers=True)
+        print("      polynomial sets chosen (-1 = quadratic tiers):", dict(zip(*[t.tolist() for t in tiers.flatten().unique(return_counts=True)])))
+        return out
     return orig(qkv, heads)
 
 
