@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--micro-batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the UNet forwards eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--codec-threads", type=int, default=0, help="host codec pool size per rank (default: host cores / ranks)")
     ap.add_argument("--no-overlap", action="store_true", help="train workload: one all-reduce after the backward instead of buckets under it")
     ap.add_argument("--projection", default="auto", choices=["auto", "codec", "dct", "device"],
                     help="data-consistency step: auto (default: device JPEG codec for --family jpeg, host codec otherwise), the "
@@ -340,9 +342,14 @@ class SampleJob:
         self.cls = {"avif": P.DDRMAVIFSampler, "webp": P.DDRMWebPSampler, "jpeg": P.DDRMJPEGSampler}[fam]
         self.y_host = synth_batch(fam, batch, res, seed=seed).pin_memory()
         self.dev, self.args = dev, args
+        self._sampler = None
 
     def sampler(self):
-        return self.cls(self.model, seed=7, micro_batches=self.args.micro_batches, projection=self.args.projection)
+        """One sampler per job: it owns the captured CUDA graphs of the micro-batch forwards."""
+        if self._sampler is None:
+            self._sampler = self.cls(self.model, seed=7, micro_batches=self.args.micro_batches, projection=self.args.projection,
+                                     use_graphs=not self.args.no_graphs)
+        return self._sampler
 
 
 def run_sample_steps(job, n_steps, warm, host_io, barrier, timed_filter=None):
@@ -361,7 +368,7 @@ def run_sample_steps(job, n_steps, warm, host_io, barrier, timed_filter=None):
         i = traj - 1
     barrier()
     ops.LAUNCHES[0] = 0
-    st["h2d"] = st["d2h"] = 0; st["codec_s"] = 0.0
+    st["h2d"] = st["d2h"] = 0; st["codec_s"] = 0.0; st["enqueue_s"] = 0.0
     codec.CPU_SECONDS[0] = 0.0
     if timed_filter is not None:
         ops.timing_begin(timed_filter)
@@ -382,23 +389,57 @@ def run_sample_steps(job, n_steps, warm, host_io, barrier, timed_filter=None):
     ms = e0.elapsed_time(e1)
     timed = ops.timing_end() if timed_filter is not None else {}
     return ms, wall, dict(launches=ops.LAUNCHES[0], h2d=st["h2d"], d2h=st["d2h"], codec_s=st["codec_s"], timed=timed,
-                          codec_cpu_s=codec.CPU_SECONDS[0], finite=bool(torch.isfinite(st["x_t"]).all()))
+                          codec_cpu_s=codec.CPU_SECONDS[0], enqueue_s=st.get("enqueue_s", 0.0), finite=bool(torch.isfinite(st["x_t"]).all()))
 
 
 def profile_one_step(job, barrier):
-    """One sampler timestep with a CUDA-event pair around EVERY op of libddpmir (outside the headline timing)."""
+    """The GPU work of one sampler timestep with a CUDA-event pair around EVERY op of libddpmir, outside the headline timing and
+    WITHOUT the host codec: the UNet forward of every micro-batch, the uint8 quantisation and the fused update on a stand-in for
+    the decoded pixels.  (Inside the real step the codec threads keep every core busy and the launcher thread's delays would be
+    booked on whatever small kernel waits for its launch.)  Also returns the polynomial-tier verdicts of every tiered attention
+    call, which the roofline needs to count the arithmetic that was actually executed."""
     import torch
     from ddpm_image_restoration_b200 import ops
     sampler = job.sampler()
-    st = sampler.begin(job.y_host.to(job.dev), job.q, steps=job.traj)
-    for i in (job.traj - 1, job.traj - 2):
-        sampler.step(st, i)
-    barrier()
-    ops.timing_begin(lambda name, tag: True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); sampler.step(st, job.traj - 3); e1.record()
-    barrier()
-    return e0.elapsed_time(e1), ops.timing_end()
+    x = job.y_host.to(job.dev)
+    chunks = sampler._chunks(x.shape[0])
+    cfg_sigma = 0.15 if job.fam == "avif" else 0.2
+
+    def gpu_step(i):
+        for s_, e_ in chunks:
+            t = torch.full((e_ - s_,), float(i) / job.traj, dtype=torch.float32, device=x.device)
+            x_theta = job.model(x[s_:e_], t, t)
+            u8 = ops.quantize_u8_hwc(x_theta)
+            ops.ddrm_update(x_theta, u8, x[s_:e_], t, cfg_sigma, seed=7, step=i)
+    with torch.no_grad():
+        gpu_step(job.traj - 1)
+        barrier()
+        ops.timing_begin(lambda name, tag: True)
+        ops.TIER_LOG = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gpu_step(job.traj - 2); e1.record()
+        barrier()
+    tiers, ops.TIER_LOG = ops.TIER_LOG, None
+    return e0.elapsed_time(e1), ops.timing_end(), tiers
+
+
+# features (padded to 128) of the polynomial-kernel tier's monomial maps, attn_lin_tc.cu: {head_dim: {degree: F}}
+LIN_FEATURES = {8: {3: 256, 4: 640, 5: 1408, 6: 3200}, 16: {3: 1024, 4: 5504}}
+LIN_SET_DEGREE = [3, 3, 3, 4, 4, 5, 6]
+
+
+def attention_executed_flops(tiers):
+    """Multiply-adds x 2 the attention calls of the profiled step really executed on the tensor cores: per (image, head), the
+    polynomial tier's two contractions (features x keys x N and rows x features x N, N = 16 / 32 value columns) or, where it
+    declined, the quadratic tier's 4 L^2 head_dim."""
+    total, hist = 0.0, {}
+    for B, L, C, heads, verdicts in tiers:
+        hd = C // heads
+        nb = 16 if hd == 8 else 32
+        for v in verdicts.flatten().tolist():
+            hist[v] = hist.get(v, 0) + 1
+            total += 4.0 * L * L * hd if v < 0 else 2.0 * 2.0 * L * LIN_FEATURES[hd][LIN_SET_DEGREE[v]] * nb
+    return total, hist
 
 
 def run_gmm(args, dev, steps_sample=None):
@@ -503,7 +544,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     host_cores = os.cpu_count() or 1
-    codec.set_threads(max(1, host_cores // world))
+    codec.set_threads(args.codec_threads if args.codec_threads else max(1, host_cores // world))
     if args.attn_expmode is not None:
         from ddpm_image_restoration_b200 import _lib
         _lib.lib().ddpmir_attention_set_expmode(args.attn_expmode)
@@ -547,10 +588,10 @@ def main():
     H = Wd = args.res
 
     if args.profile_ops and rank == 0:
-        step_ms, timed = profile_one_step(jobs[-1], barrier)
+        step_ms, timed, _ = profile_one_step(jobs[-1], barrier)
         classes, groups = summarize_ops(timed, pk)
         tot = sum(c["ms"] for c in classes.values())
-        print(f"# per-op CUDA-event times of one sampler step ({step_ms:.1f} ms total, {tot:.1f} ms inside libddpmir ops)", file=sys.stderr)
+        print(f"# per-op CUDA-event times of the GPU work of one sampler step ({step_ms:.1f} ms total, {tot:.1f} ms inside libddpmir ops)", file=sys.stderr)
         for (name, tag), g_ in groups[:48]:
             rate = f"{g_['tflops']:8.1f} TFLOP/s" if "tflops" in g_ else f"{g_['gbs']:8.0f} GB/s"
             print(f"#   {g_['ms']:9.3f} ms  x{g_['calls']:3d}  {rate}  {name:16s} {tag}", file=sys.stderr)
@@ -578,7 +619,7 @@ def main():
     roof = roof_convs = roof_attn = hbm_table = None
     if rank == 0:
         job = jobs[-1]
-        step_ms, timed = profile_one_step(job, lambda: torch.cuda.synchronize())
+        step_ms, timed, tiers = profile_one_step(job, lambda: torch.cuda.synchronize())
         classes, groups = summarize_ops(timed, pk)
         conv_ms = sum(classes[n]["ms"] for n in ("conv3x3", "gemm") if n in classes)
         conv_fl = sum(g_["tflops"] * g_["ms"] for (n, _), g_ in groups if n in ("conv3x3", "gemm"))   # TFLOP/s * ms = GFLOP
@@ -587,20 +628,28 @@ def main():
                           "achieved": conv_fl / conv_ms, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                           "frac": conv_fl / conv_ms / pk["tf_sustained"], "ms_per_step": conv_ms,
                           "gflop_per_step": conv_fl, "launches": sum(classes[n]["calls"] for n in ("conv3x3", "gemm") if n in classes)}
+        exec_fl, set_hist = attention_executed_flops(tiers)
         if "attention" in classes:
             a = classes["attention"]
             roof_attn = {"ms_per_step": a["ms"], "launches": a["calls"], "reference_equivalent_tflops": a["tflops"],
-                         "note": "4 L^2 C FLOP of the reference's softmax attention per call / measured time.  With the "
-                                 "polynomial-kernel tier (attn_lin.cu, logit bound <= 2) the arithmetic actually executed is "
-                                 "O(L F head_dim), so this is an equivalent rate, not tensor-pipe utilisation"}
+                         "polynomial_sets": {str(k): v for k, v in sorted(set_hist.items())},
+                         "note": "reference_equivalent = 4 L^2 C FLOP of the reference's softmax attention per call / measured time.  "
+                                 "(image, head) pairs whose logit bound fits a polynomial set (attn_lin*.cu) cost O(L F head_dim) "
+                                 "instead, so this is an equivalent rate, not tensor-pipe utilisation; polynomial_sets counts the "
+                                 "verdicts of the tiered calls (-1 = quadratic tiers)"}
         hbm_table = {n: {"ms_per_step": c["ms"], "calls": c["calls"], "gbs": c["gbs"], "frac_of_hbm_peak": c["frac_of_hbm_peak"]}
-                     for n, c in classes.items() if c["kind"] == "bytes" and c["ms"] > 0}
+                     for n, c in classes.items() if c["kind"] == "bytes" and c["ms"] > 0 and c.get("gbs", 0) > 0}
         # the dominant kernel = the (op, shape) group with the most time in the step
         (dname, dtag), dg = groups[0]
         key = f"{dname}{list(dtag)}"
         traffic, tsrc = traffic_from_profile(key)
         kind, work = op_work(dname, dtag)
         avg_ms = dg["ms"] / dg["calls"]
+        if dname == "attention":
+            # executed tensor-core arithmetic of exactly these calls (their verdicts), not the reference's 4 L^2 C
+            mine = [t_ for t_ in tiers if (t_[0], t_[1], t_[2], t_[3]) == tuple(dtag)]
+            if mine:
+                work = attention_executed_flops(mine)[0] / len(mine)
         if kind == "flops":
             ach = work / (avg_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
@@ -613,9 +662,13 @@ def main():
                      "traffic": traffic, "traffic_source": tsrc, "algorithmic_work": work,
                      "profiled_step_ms": step_ms})
         if dname == "attention":
-            heads = dtag[3]
-            roof["note"] = ("attention call = pre-pass + polynomial-kernel tier (attn_lin.cu) + quadratic tiers for what it declines; "
-                            "achieved = the reference's 4 L^2 C FLOP / time (an equivalent rate: see roofline_attention.note)")
+            roof["reference_equivalent_tflops"] = op_work(dname, dtag)[1] / (avg_ms * 1e-3) / 1e12
+            roof["note"] = ("one attention call of the full-resolution blocks = pre-pass + polynomial-kernel tier (attn_lin_tc.cu: "
+                            "attn_lin_state_tc_kernel, attn_lin_reduce_tc_kernel, attn_lin_out_tc_kernel) + the quadratic tiers for what "
+                            "it declines.  achieved = the tensor-core FLOP these kernels EXECUTED (2 x 2 L F N per (image, head), F "
+                            "features, N value columns) / time: the kernels are bound by generating the features on the fp32 pipe "
+                            "(one multiply + half a convert per feature), the tensor pipe follows.  reference_equivalent_tflops = the "
+                            "reference's 4 L^2 C FLOP / the same time")
 
     unet_tflops = UNET_GF[jobs[0].fam] * B_total / 1e3 / (ms_per_step / 1e3) if (args.res == 256 and len(jobs) == 1) else None
     cpu = None
@@ -650,6 +703,7 @@ def main():
             "unet_tflops": unet_tflops, "unet_frac_of_bf16_sustained": (unet_tflops / pk["tf_sustained"]) if unet_tflops else None,
             "codec_wait_ms_per_step": sum(s_["codec_s"] for s_ in stats_f) * 1e3 / K,
             "codec_cpu_ms_per_step": sum(s_["codec_cpu_s"] for s_ in stats_f) * 1e3 / K,
+            "launch_host_ms_per_step": sum(s_["enqueue_s"] for s_ in stats_f) * 1e3 / K,
             "wall_ms_per_step": sum(wall_f), "finite": all(s_["finite"] for s_ in stats_f), "secondary": secondary,
         }
         print(json.dumps(line), flush=True)

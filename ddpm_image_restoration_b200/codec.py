@@ -12,6 +12,7 @@ Unlike the reference's avif_compress there is no silent JPEG fallback: an AVIF f
 import concurrent.futures as cf
 import io
 import os
+import sys
 import threading
 import time
 
@@ -59,6 +60,11 @@ def set_threads(n):
         _POOL.shutdown(wait=True)
     _POOL = cf.ThreadPoolExecutor(max_workers=max(1, int(n)), thread_name_prefix="ddpmir-codec", initializer=_codec_thread_init)
     _POOL_THREADS = max(1, int(n))
+    # The codec threads run short Python sections (Pillow's save/open wrappers) between long GIL-free encodes; with the default
+    # 5 ms switch interval the thread that launches GPU work queues for the interpreter lock behind them (measured: 10 ms per
+    # micro-batch launch that takes 0.2 ms uncontended).  A short interval hands the lock over promptly.
+    if sys.getswitchinterval() > 2e-4:
+        sys.setswitchinterval(2e-4)
 
 
 def pool():

@@ -16,6 +16,7 @@ def _stream():
 
 # ---- instrumentation (bench.py): kernel-launch counter and CUDA-event timing of selected ops ----------------
 LAUNCHES = [0]          # kernels of libddpmir.so launched through this module
+TIER_LOG = None         # bench.py's profiled step sets this to a list: (B, L, C, heads, verdicts [B, heads] on the host) per tiered attention call
 _TIMED = {}             # op name -> list of (start_event, end_event, tag)
 _TIMED_FILTER = None    # callable(name, tag) -> bool, or None
 
@@ -410,6 +411,8 @@ def attention_prescaled(qkv, heads, return_tiers=False):
         with _timed("attention", (B, L, C, heads), 10):
             _lib.check(_lib.lib().ddpmir_attention_prescaled_f16(_p(qkv), B, L, C, heads, _p(ws), _p(out), _stream()),
                        "attention_prescaled_f16")
+        if TIER_LOG is not None:
+            TIER_LOG.append((B, L, C, heads, attention_tiers(ws, B, L, heads).cpu()))      # synchronises: profiling only
         return (out, attention_tiers(ws, B, L, heads)) if return_tiers else out
     if qkv.dtype != torch.bfloat16:
         raise TypeError("attention_prescaled is the bf16 / binary16 inference path")

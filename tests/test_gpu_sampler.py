@@ -288,3 +288,27 @@ def test_ddrm_jpeg_sampler_device_codec_equals_host_codec():
             assert abs(R.psnr(dev, clean) - R.psnr(host, clean)) < 0.3, (quality, precision)
     with pytest.raises(ValueError):
         P.DDRMWebPSampler(load_model("webp"), projection="device")
+
+
+def test_sampler_cuda_graphs_equal_eager_launches():
+    """The sampler replays a captured CUDA graph of every micro-batch's UNet forward + quantisation (a forward is ~450 launches and
+    the launching thread competes with the codec pool).  Same trajectory as eager launches (fp32 check mode; the GroupNorm
+    statistics accumulate with atomics, so two runs agree to rounding, not bit for bit), and the graphs must really be used and
+    reused."""
+    import ddpm_image_restoration_b200 as P
+    m = load_model("webp").set_precision("fp32")
+    clean = W.synthetic_images(4, 64, 64)
+    y = R.codec_roundtrip(clean, 10, "webp")
+    outs = []
+    for use in (True, False):
+        smp = P.DDRMWebPSampler(m, seed=5, micro_batches=2, use_graphs=use)
+        outs.append(smp.sample(y.cuda(), 10, steps=4).cpu())
+        captured = [v for v in smp._graphs.values() if isinstance(v, dict) and "graph" in v]
+        assert len(captured) == (2 if use else 0)
+        if use:     # a second trajectory on the same sampler reuses the graphs
+            again = smp.sample(y.cuda(), 10, steps=4).cpu()
+            assert abs(R.psnr(again, clean) - R.psnr(outs[0], clean)) < 0.02
+            assert len([v for v in smp._graphs.values() if isinstance(v, dict) and "graph" in v]) == 2
+    assert torch.isfinite(outs[0]).all()
+    assert abs(R.psnr(outs[0], clean) - R.psnr(outs[1], clean)) < 0.02
+    assert R.psnr(outs[0], outs[1]) > 38.0
