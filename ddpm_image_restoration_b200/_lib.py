@@ -83,6 +83,10 @@ _SIGNATURES = {
     "ddpmir_out_conv_tanh_backward": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "ddpmir_mse_backward": (c_int, [_P, _P, c_int64, c_float, _P, c_int, _P]),
     "ddpmir_freq_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
+    "ddpmir_fft2_loss_terms": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "ddpmir_fft2_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
+    "ddpmir_edge_loss": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_edge_loss_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "ddpmir_ssim_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
     "ddpmir_huber": (c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
     "ddpmir_huber_backward": (c_int, [_P, _P, c_int64, c_float, c_float, _P, c_int, _P]),

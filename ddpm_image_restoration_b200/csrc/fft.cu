@@ -116,7 +116,7 @@ row_ifft_blend_kernel(const float2* __restrict__ ws, const float* __restrict__ x
 // sum (angle P - angle T)^2.  The row pass transformed x*0.5+0.5 (see row_fft_affine_kernel).
 __global__ void __launch_bounds__(FFT_THREADS)
 col_loss_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, int H, int W, int cols_per_cta,
-                double* __restrict__ acc) {
+                double* __restrict__ acc, int full) {
     extern __shared__ float2 sm[];
     float2* a = sm;
     float2* b = sm + FFT_ELEMS;
@@ -138,7 +138,11 @@ col_loss_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, in
         const float2 P = a[i], T = a[nb * H + i];
         const float dm = sqrtf(P.x * P.x + P.y * P.y) - sqrtf(T.x * T.x + T.y * T.y);
         const float dp = atan2f(P.y, P.x) - atan2f(T.y, T.x);
-        sm2 = fmaf(dm, dm, sm2); sp2 = fmaf(dp, dp, sp2);
+        // full = 1: the sums run over the whole fft2 spectrum (avif.py:150-158); its columns W/2+1 .. W-1 mirror 1 .. W/2-1
+        // (conjugate symmetry of a real image: same magnitudes, negated angles), so those columns count twice
+        const int col = c0 + i / H;
+        const float wgt = (full && col > 0 && 2 * col < W) ? 2.f : 1.f;
+        sm2 = fmaf(wgt * dm, dm, sm2); sp2 = fmaf(wgt * dp, dp, sp2);
     }
     sm2 = warp_sum(sm2); sp2 = warp_sum(sp2);
     __shared__ float red[2][FFT_THREADS / 32];
@@ -157,7 +161,7 @@ col_loss_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, in
 // d/dp = Re IDFT_unnormalised(G).  Columns > W/2 of wg stay zero (memset by the host wrapper).
 __global__ void __launch_bounds__(FFT_THREADS)
 col_loss_bwd_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt, float2* __restrict__ wg, int H, int W,
-                    int cols_per_cta, float w_mag, float w_phase) {
+                    int cols_per_cta, float w_mag, float w_phase, int full) {
     extern __shared__ float2 sm[];
     float2* a = sm;
     float2* b = sm + FFT_ELEMS;
@@ -178,9 +182,11 @@ col_loss_bwd_kernel(const float2* __restrict__ wp, const float2* __restrict__ wt
         const float2 P = a[i], T = a[nb * H + i];
         const float mp = sqrtf(P.x * P.x + P.y * P.y), mt = sqrtf(T.x * T.x + T.y * T.y);
         float gx = 0.f, gy = 0.f;
+        const int col = c0 + i / H;
+        const float wgt = (full && col > 0 && 2 * col < W) ? 2.f : 1.f;            // mirrored columns of the full spectrum
         if (mp > 0.f) {
-            const float cm = 2.f * w_mag * (mp - mt) / mp;                                  // d|P| = (Re, Im)/|P|
-            const float cp = 2.f * w_phase * (atan2f(P.y, P.x) - atan2f(T.y, T.x)) / (mp * mp);   // d angle = (-Im, Re)/|P|^2
+            const float cm = wgt * 2.f * w_mag * (mp - mt) / mp;                                  // d|P| = (Re, Im)/|P|
+            const float cp = wgt * 2.f * w_phase * (atan2f(P.y, P.x) - atan2f(T.y, T.x)) / (mp * mp);   // d angle = (-Im, Re)/|P|^2
             gx = cm * P.x - cp * P.y;
             gy = cm * P.y + cp * P.x;
         }
@@ -291,8 +297,8 @@ extern "C" int ddpmir_phase_consistency(const float* x, const float* phasor, flo
     return DDPMIR_OK;
 }
 
-extern "C" int ddpmir_freq_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
-                                      float* ws_target, double* acc2, ddpmir_stream_t stream) {
+static int freq_loss_terms_impl(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
+                                float* ws_target, double* acc2, int full, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(pred && target && ws_pred && ws_target && acc2, "freq_loss_terms: null pointer");
     int rc = check_shape(planes, H, W);
     if (rc) return rc;
@@ -308,14 +314,22 @@ extern "C" int ddpmir_freq_loss_terms(const float* pred, const float* target, in
     row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(target, (float2*)ws_target, rows, W, rpc);
     DDPMIR_LAUNCH_CHECK();
     col_loss_kernel<<<dim3(ceil_div(W / 2 + 1, cpc), planes), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_pred, (const float2*)ws_target,
-                                                                                          H, W, cpc, acc2);
+                                                                                          H, W, cpc, acc2, full);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }
+extern "C" int ddpmir_freq_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
+                                      float* ws_target, double* acc2, ddpmir_stream_t stream) {
+    return freq_loss_terms_impl(pred, target, planes, H, W, ws_pred, ws_target, acc2, 0, stream);
+}
+extern "C" int ddpmir_fft2_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
+                                      float* ws_target, double* acc2, ddpmir_stream_t stream) {
+    return freq_loss_terms_impl(pred, target, planes, H, W, ws_pred, ws_target, acc2, 1, stream);
+}
 
 // dpred += d/dpred [ w_mag * sum (|P|-|T|)^2 + w_phase * sum (angle P - angle T)^2 ],  P = rfft2(pred*0.5+0.5)
-extern "C" int ddpmir_freq_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
-                                         float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream) {
+static int freq_loss_backward_impl(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
+                                   float* ws_pred, float* ws_target, float* ws_grad, float* dpred, int full, ddpmir_stream_t stream) {
     DDPMIR_CHECK_ARG(pred && target && ws_pred && ws_target && ws_grad && dpred, "freq_loss_backward: null pointer");
     int rc = check_shape(planes, H, W);
     if (rc) return rc;
@@ -330,9 +344,17 @@ extern "C" int ddpmir_freq_loss_backward(const float* pred, const float* target,
     row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(pred, (float2*)ws_pred, rows, W, rpc);
     row_fft_affine_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>(target, (float2*)ws_target, rows, W, rpc);
     col_loss_bwd_kernel<<<dim3(ceil_div(W / 2 + 1, cpc), planes), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_pred, (const float2*)ws_target,
-                                                                                              (float2*)ws_grad, H, W, cpc, w_mag, w_phase);
+                                                                                              (float2*)ws_grad, H, W, cpc, w_mag, w_phase, full);
     // chain rule of p01 = 0.5 * pred + 0.5
     row_ifft_accum_kernel<<<ceil_div(rows, rpc), FFT_THREADS, SMEM_BYTES, st>>>((const float2*)ws_grad, dpred, rows, W, rpc, 0.5f);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
+}
+extern "C" int ddpmir_freq_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
+                                         float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream) {
+    return freq_loss_backward_impl(pred, target, planes, H, W, w_mag, w_phase, ws_pred, ws_target, ws_grad, dpred, 0, stream);
+}
+extern "C" int ddpmir_fft2_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
+                                         float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream) {
+    return freq_loss_backward_impl(pred, target, planes, H, W, w_mag, w_phase, ws_pred, ws_target, ws_grad, dpred, 1, stream);
 }

@@ -240,6 +240,50 @@ color_l1_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ ta
 
 __global__ void scale_kernel(const double* __restrict__ acc, double scale, float* __restrict__ out) { out[0] = (float)(acc[0] * scale); }
 
+// gradient_loss of avif_frequency_aware_loss (avif.py:136-144) on the [0,1] images x*0.5+0.5: sums of
+// (|x_i - x_down| - |y_i - y_down|)^2 (acc[0], over H-1 rows) and (|x_i - x_right| - |y_i - y_right|)^2 (acc[1], over W-1 columns)
+__global__ void __launch_bounds__(256)
+edge_loss_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int W, long long n, double* __restrict__ acc) {
+    float sv = 0.f, sh = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W), h = (int)((i / W) % H);
+        const float xi = x[i] * 0.5f, yi = y[i] * 0.5f;            // the +0.5 cancels in every difference
+        if (h + 1 < H) { const float d = fabsf(xi - x[i + W] * 0.5f) - fabsf(yi - y[i + W] * 0.5f); sv = fmaf(d, d, sv); }
+        if (w + 1 < W) { const float d = fabsf(xi - x[i + 1] * 0.5f) - fabsf(yi - y[i + 1] * 0.5f); sh = fmaf(d, d, sh); }
+    }
+    sv = warp_sum(sv); sh = warp_sum(sh);
+    __shared__ float red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = sh; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0;
+        for (int k = 0; k < 8; ++k) v += (double)red[threadIdx.x][k];
+        atomicAdd(&acc[threadIdx.x], v);
+    }
+}
+// dx (+)= wv d acc[0]/dx + wh d acc[1]/dx: every pixel collects the (up to four) difference terms it takes part in.
+// d |a - b| / da = sign(a - b) (0 at a == b, torch.abs's convention).
+__global__ void __launch_bounds__(256)
+edge_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int W, long long n, float wv, float wh,
+                     float* __restrict__ dx, int accumulate) {
+    auto term = [](float xa, float xb, float ya, float yb) {      // d/d xa of (|xa - xb| - |ya - yb|)^2
+        const float dxv = xa - xb;
+        const float sgn = dxv > 0.f ? 1.f : (dxv < 0.f ? -1.f : 0.f);
+        return 2.f * (fabsf(dxv) - fabsf(ya - yb)) * sgn;
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W), h = (int)((i / W) % H);
+        const float xi = x[i] * 0.5f, yi = y[i] * 0.5f;
+        float g = 0.f;
+        if (h + 1 < H) g += wv * term(xi, x[i + W] * 0.5f, yi, y[i + W] * 0.5f);
+        if (h > 0) g += wv * term(xi, x[i - W] * 0.5f, yi, y[i - W] * 0.5f);
+        if (w + 1 < W) g += wh * term(xi, x[i + 1] * 0.5f, yi, y[i + 1] * 0.5f);
+        if (w > 0) g += wh * term(xi, x[i - 1] * 0.5f, yi, y[i - 1] * 0.5f);
+        g *= 0.5f;                                                 // chain rule of x01 = 0.5 x + 0.5
+        dx[i] = accumulate ? dx[i] + g : g;
+    }
+}
+
 }  // namespace
 
 extern "C" int ddpmir_mse(const float* a, const float* b, int64_t n, float* out_scalar, double* ws, ddpmir_stream_t stream) {
@@ -338,6 +382,31 @@ extern "C" int ddpmir_ssim_backward(const float* x, const float* y, int planes, 
     // mean over planes*OH*OW outputs; chain rule of x01 = 0.5 x + 0.5
     const float coef = (float)(0.5 * (double)weight / ((double)planes * OH * OW));
     ssim_bwd_scatter_kernel<<<g2, 256, 0, st>>>(x, y, ws, planes, H, W, clamp01, g, coef, dx);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+
+// gradient_loss of avif_frequency_aware_loss (avif.py:136-146): acc2[0] / acc2[1] = the two sums of squares over [planes, H, W]
+// images (see edge_loss_kernel); the caller divides by planes*(H-1)*W and planes*H*(W-1) (F.mse_loss means).
+extern "C" int ddpmir_edge_loss(const float* pred, const float* target, int planes, int H, int W, double* acc2, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(pred && target && acc2 && planes > 0 && H > 1 && W > 1, "edge_loss: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(acc2, 0, 2 * sizeof(double), st);
+    const long long n = (long long)planes * H * W;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    edge_loss_kernel<<<grid, 256, 0, st>>>(pred, target, H, W, n, acc2);
+    DDPMIR_LAUNCH_CHECK();
+    return DDPMIR_OK;
+}
+// dpred (+)= w_v d acc2[0]/dpred + w_h d acc2[1]/dpred
+extern "C" int ddpmir_edge_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_v, float w_h,
+                                         float* dpred, int accumulate, ddpmir_stream_t stream) {
+    DDPMIR_CHECK_ARG(pred && target && dpred && planes > 0 && H > 1 && W > 1, "edge_loss_backward: bad arguments");
+    const long long n = (long long)planes * H * W;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    edge_loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, H, W, n, w_v, w_h, dpred, accumulate);
     DDPMIR_LAUNCH_CHECK();
     return DDPMIR_OK;
 }

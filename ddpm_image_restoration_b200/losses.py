@@ -6,6 +6,7 @@ training.Trainer calls for the training step (webp_training.py:476-537).
   color_loss                conv_deep.ipynb#c0:L60-73        0.25 L1_R + 0.5 L1_G + 0.25 L1_B on clamped [0,1] images
   color_preservation_loss   0409_method.ipynb#c0:L64-82      color_loss + 0.5 (1 - SSIM)
   frequency_aware_loss      webp_training.py:105-132         MSE + 0.5 sum_c [MSE |rfft2| + 0.5 MSE angle rfft2] + 0.3 (1 - SSIM)
+  avif_frequency_aware_loss avif.py:126-164                  MSE + 0.3 sum_c [MSE |fft2| + 0.3 MSE angle fft2] + 0.4 (1 - SSIM) + 0.2 edge
 
 SSIM follows pytorch_msssim.ssim's published algorithm (gaussian window 11, sigma 1.5, valid filtering); the package is
 not pinned by the reference nor installed here, so that term's parity is against the oracle's restatement only.
@@ -42,6 +43,21 @@ def frequency_aware_loss(pred, target):
     count = float(B * H * (W // 2 + 1))                             # elements of one channel's rfft2
     freq = (terms[0] + 0.5 * terms[1]).float() / count
     return spatial + 0.5 * freq + 0.3 * (1.0 - ops.ssim(pred, target, clamp01=False))
+
+
+def avif_frequency_aware_loss(pred, target):
+    """avif.py:126-164: spatial MSE + 0.3 * sum over channels of [MSE |fft2| + 0.3 MSE angle fft2] + 0.4 (1 - SSIM) + 0.2 *
+    gradient_loss (MSE of the absolute vertical / horizontal neighbour differences), on the [0,1] images."""
+    pred, target = _prep(pred, target)
+    B, C, H, W = pred.shape
+    if C != 3:
+        raise ValueError("avif_frequency_aware_loss sums over the 3 colour channels")
+    spatial = ops.mse(pred, target)
+    terms = ops.freq_loss_terms(pred, target, full_spectrum=True)   # sums over all B*3 planes, full spectrum
+    freq = (terms[0] + 0.3 * terms[1]).float() / float(B * H * W)   # one channel's fft2 has B*H*W coefficients
+    edge = ops.edge_loss_terms(pred, target)
+    edge_loss = (edge[0] / float(B * C * (H - 1) * W) + edge[1] / float(B * C * H * (W - 1))).float()
+    return spatial + 0.3 * freq + 0.4 * (1.0 - ops.ssim(pred, target, clamp01=False)) + 0.2 * edge_loss
 
 
 def huber_loss(pred, target, delta=1.0):

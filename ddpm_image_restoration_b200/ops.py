@@ -206,7 +206,7 @@ def svd_lowrank(x, k, sweeps=0):
     B, C, H, W = x.shape
     out = torch.empty_like(x)
     ws = torch.empty((B * C * (H * W + H * H + 2 * H),), dtype=torch.float32, device=x.device)
-    with _timed("svd_lowrank", (B * C, H, W, int(k)), 1):
+    with _timed("svd_lowrank", (B * C, H, W, int(k)), 3):     # Jacobi sweeps + the two reconstruction GEMMs
         _lib.check(_lib.lib().ddpmir_svd_lowrank(_p(_f32(x, "x")), B * C, H, W, int(k), _p(out), _p(ws), int(sweeps), _stream()),
                    "svd_lowrank")
     return out
@@ -252,15 +252,25 @@ def ssim(x, y, clamp01=False):
     return out[0]
 
 
-def freq_loss_terms(pred, target):
-    """Returns a float64 tensor [2]: sum of squared rfft2-magnitude differences and of squared phase differences."""
+def freq_loss_terms(pred, target, full_spectrum=False):
+    """Returns a float64 tensor [2]: sum of squared rfft2-magnitude differences and of squared phase differences
+    (full_spectrum: over the whole fft2 spectrum, avif.py:150-158)."""
     B, C, H, W = pred.shape
     wp = torch.empty((B * C, H, W, 2), dtype=torch.float32, device=pred.device)
     wt = torch.empty_like(wp)
     acc = torch.empty((2,), dtype=torch.float64, device=pred.device)
-    _lib.check(_lib.lib().ddpmir_freq_loss_terms(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B * C, H, W, _p(wp), _p(wt),
-                                                 _p(acc), _stream()), "freq_loss_terms")
+    fn = _lib.lib().ddpmir_fft2_loss_terms if full_spectrum else _lib.lib().ddpmir_freq_loss_terms
+    _lib.check(fn(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B * C, H, W, _p(wp), _p(wt), _p(acc), _stream()), "freq_loss_terms")
     LAUNCHES[0] += 3
+    return acc
+
+
+def edge_loss_terms(pred, target):
+    """Returns a float64 tensor [2]: the two sums of squares of avif.py's gradient_loss (vertical, horizontal neighbour pairs)."""
+    B, C, H, W = pred.shape
+    acc = torch.empty((2,), dtype=torch.float64, device=pred.device)
+    _lib.check(_lib.lib().ddpmir_edge_loss(_p(_f32(pred, "pred")), _p(_f32(target, "target")), B * C, H, W, _p(acc), _stream()), "edge_loss")
+    LAUNCHES[0] += 1
     return acc
 
 

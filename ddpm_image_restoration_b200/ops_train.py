@@ -187,6 +187,29 @@ def frequency_aware_loss_backward(pred, target, upstream=1.0):
     return dpred
 
 
+def avif_frequency_aware_loss_backward(pred, target, upstream=1.0):
+    """d avif_frequency_aware_loss(pred, target) / d pred  (avif.py:126-164), scaled by `upstream`."""
+    B, C, H, W = pred.shape
+    dpred = torch.empty_like(pred)
+    lib = _lib.lib()
+    _lib.check(lib.ddpmir_mse_backward(_p(_f32(pred, "pred")), _p(_f32(target, "target")), pred.numel(), float(upstream), _p(dpred), 0,
+                                       _stream()), "mse_backward")
+    count = float(B * H * W)
+    wp = torch.empty((B * C, H, W, 2), dtype=F32, device=pred.device)
+    wt = torch.empty_like(wp)
+    wg = torch.empty_like(wp)
+    # 0.3 * sum_c [mse_mag + 0.3 * mse_phase], each mse a mean over `count` coefficients of the full spectrum
+    _lib.check(lib.ddpmir_fft2_loss_backward(_p(pred), _p(target), B * C, H, W, upstream * 0.3 / count, upstream * 0.09 / count, _p(wp),
+                                             _p(wt), _p(wg), _p(dpred), _stream()), "fft2_loss_backward")
+    ws = torch.empty((B * C * 3 * (H - 10) * (W - 10),), dtype=F32, device=pred.device)
+    _lib.check(lib.ddpmir_ssim_backward(_p(pred), _p(target), B * C, H, W, 0, -0.4 * upstream, _p(dpred), _p(ws), _stream()),
+               "ssim_backward")
+    _lib.check(lib.ddpmir_edge_loss_backward(_p(pred), _p(target), B * C, H, W, 0.2 * upstream / float(B * C * (H - 1) * W),
+                                             0.2 * upstream / float(B * C * H * (W - 1)), _p(dpred), 1, _stream()), "edge_loss_backward")
+    LAUNCHES[0] += 8
+    return dpred
+
+
 def color_preservation_loss_backward(pred, target, upstream=1.0, include_ssim=True, out=None):
     """d color_preservation_loss(pred, target) / d pred (0409_method.ipynb#c0:L64-82: colour L1 + 0.5 (1 - SSIM) on images
     clamped to [0,1]), scaled by `upstream`; accumulated into `out` when given."""

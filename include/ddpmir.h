@@ -139,6 +139,16 @@ int ddpmir_ssim(const float* x, const float* y, int planes, int H, int W, int cl
 int ddpmir_freq_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
                            float* ws_target, double* acc2, ddpmir_stream_t stream);
 
+/* The same two sums over the FULL fft2 spectrum, the frequency terms of avif_frequency_aware_loss (avif.py:148-158:
+ * torch.fft.fft2 instead of rfft2).  Computed on the half spectrum with the mirrored columns counted twice. */
+int ddpmir_fft2_loss_terms(const float* pred, const float* target, int planes, int H, int W, float* ws_pred,
+                           float* ws_target, double* acc2, ddpmir_stream_t stream);
+
+/* gradient_loss of avif_frequency_aware_loss (avif.py:136-146) on the [0,1] images: acc2[0] = sum over the H-1 vertical
+ * neighbour pairs of (|x - x_down| - |y - y_down|)^2, acc2[1] = the same over the W-1 horizontal pairs; the two F.mse_loss
+ * means are acc2[0] / (planes (H-1) W) and acc2[1] / (planes H (W-1)). */
+int ddpmir_edge_loss(const float* pred, const float* target, int planes, int H, int W, double* acc2, ddpmir_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------ */
 /* UNet kernels                                                                                            */
 /* ------------------------------------------------------------------------------------------------------ */
@@ -378,6 +388,12 @@ int ddpmir_freq_loss_backward(const float* pred, const float* target, int planes
                               float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream);
 int ddpmir_ssim_backward(const float* x, const float* y, int planes, int H, int W, int clamp01, float weight, float* dx, float* ws,
                          ddpmir_stream_t stream);
+/* Gradients of the two AVIF-specific terms (avif.py:126-164): the full-spectrum frequency terms (same contract as
+ * ddpmir_freq_loss_backward) and dpred (+)= w_v d acc2[0]/dpred + w_h d acc2[1]/dpred of ddpmir_edge_loss. */
+int ddpmir_fft2_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_mag, float w_phase,
+                              float* ws_pred, float* ws_target, float* ws_grad, float* dpred, ddpmir_stream_t stream);
+int ddpmir_edge_loss_backward(const float* pred, const float* target, int planes, int H, int W, float w_v, float w_h,
+                              float* dpred, int accumulate, ddpmir_stream_t stream);
 
 /* nn.HuberLoss(reduction='mean', delta) (0409_method.ipynb#c0:L438, 567) over n elements, and its gradient
  * da (+)= weight * d huber / da.  n % 4 == 0 for the forward; ws: one double. */

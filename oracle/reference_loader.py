@@ -118,6 +118,25 @@ def load_conv_deep_color_loss():
     return ns
 
 
+def load_avif_loss(ssim_fn):
+    """avif.py lines 126-164 (`avif_frequency_aware_loss`), executed verbatim.  Its `ssim` is pytorch_msssim's (not installed,
+    no version pinned by the reference): the caller passes the stand-in, so everything BUT the SSIM term is pinned by this."""
+    _install_stubs()
+    lines = open(os.path.join(REF_ROOT, "avif.py"), encoding="utf-8").read().split("\n")
+    ns = _exec(_slice(lines, [(126, 164)]), "ref_avif_loss", prelude="import torch\nimport torch.nn.functional as F\n")
+    ns["ssim"] = ssim_fn
+    return ns
+
+
+def load_webp_loss(ssim_fn):
+    """webp_training.py lines 105-132 (`frequency_aware_loss`), executed verbatim with the SSIM stand-in (see load_avif_loss)."""
+    _install_stubs()
+    lines = open(os.path.join(REF_ROOT, "webp_training.py"), encoding="utf-8").read().split("\n")
+    ns = _exec(_slice(lines, [(105, 132)]), "ref_webp_loss", prelude="import torch\nimport torch.nn.functional as F\n")
+    ns["ssim"] = ssim_fn
+    return ns
+
+
 def load_dct_processor():
     """experiments/code/dct.ipynb cell 2 lines 43-139 (`DCTProcessor`: the pure-torch JPEG simulator with quant tables)."""
     _install_stubs()

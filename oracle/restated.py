@@ -483,6 +483,23 @@ def frequency_aware_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tens
     return spatial + 0.5 * freq + 0.3 * (1.0 - ssim(p01, t01, 1.0))
 
 
+def avif_frequency_aware_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """avif.py:126-164 (SSIM restated, see `ssim`): full fft2 spectrum, gradient (edge) term, weights 0.3 / 0.4 / 0.2."""
+    spatial = F.mse_loss(pred, target)
+    p01, t01 = pred * 0.5 + 0.5, target * 0.5 + 0.5
+
+    def gradient_loss(x, y):                                           # avif.py:136-144
+        gxx = torch.abs(x[:, :, :-1, :] - x[:, :, 1:, :]); gxy = torch.abs(x[:, :, :, :-1] - x[:, :, :, 1:])
+        gyx = torch.abs(y[:, :, :-1, :] - y[:, :, 1:, :]); gyy = torch.abs(y[:, :, :, :-1] - y[:, :, :, 1:])
+        return F.mse_loss(gxx, gyx) + F.mse_loss(gxy, gyy)
+    edge = gradient_loss(p01, t01)
+    freq = 0
+    for c in range(3):
+        fp, ft = torch.fft.fft2(p01[:, c]), torch.fft.fft2(t01[:, c])
+        freq = freq + F.mse_loss(torch.abs(fp), torch.abs(ft)) + 0.3 * F.mse_loss(torch.angle(fp), torch.angle(ft))
+    return spatial + 0.3 * freq + 0.4 * (1.0 - ssim(p01, t01, 1.0)) + 0.2 * edge
+
+
 def training_step_reference(sd: SD, xt, t, x0, family: str = "webp"):
     """Loss and gradients of one training step (webp_training.py:511-521, dropout disabled) by torch.autograd."""
     params = {k: (v.clone().requires_grad_() if v.dtype.is_floating_point and not k.endswith("dct_matrix") else v) for k, v in sd.items()}

@@ -239,6 +239,24 @@ def test_frequency_aware_loss_backward(T):
     assert rel(got, pred.grad) < 2e-3      # the phase term's gradient ~ 1/|P| is ill-conditioned at small coefficients
 
 
+def test_avif_frequency_aware_loss_forward_and_backward(T):
+    """avif.py:126-164 (full fft2 spectrum, gradient-edge term, weights 0.3 / 0.4 / 0.2): value and gradient against torch.autograd
+    over the oracle's restatement (pinned against the verbatim reference in test_oracle_vs_reference.py)."""
+    import ddpm_image_restoration_b200 as P
+    gen = g(5)
+    for hw in ((32, 32), (64, 32)):
+        target = torch.rand(2, 3, *hw, generator=gen) * 2 - 1
+        pred = (target + 0.2 * torch.randn(2, 3, *hw, generator=gen)).requires_grad_()
+        loss = R.avif_frequency_aware_loss(pred, target)
+        loss.backward()
+        got = float(P.avif_frequency_aware_loss(pred.detach().cuda(), target.cuda()))
+        assert abs(got - float(loss)) < 1e-3 * abs(float(loss)), (got, float(loss))
+        grad = T.avif_frequency_aware_loss_backward(pred.detach().cuda(), target.cuda()).cpu()
+        assert rel(grad, pred.grad) < 2e-3      # the phase term's gradient ~ 1/|P| is ill-conditioned at small coefficients
+        grad2 = T.avif_frequency_aware_loss_backward(pred.detach().cuda(), target.cuda(), upstream=0.5).cpu()
+        assert rel(grad2, 0.5 * pred.grad) < 2e-3
+
+
 def test_adamw_and_clip(T):
     torch.manual_seed(0)
     ps = [torch.randn(1000), torch.randn(37, 5)]

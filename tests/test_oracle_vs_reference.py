@@ -80,3 +80,16 @@ def test_m0409_model_against_reference():
         assert rel(R.unet0409_forward(sd, x, t), m(x, t)) < 2e-6
         lvl = torch.tensor([0.3, 0.9])
         assert rel(R.unet0409_forward(sd, x, t, lvl), m(x, t, lvl)) < 2e-6
+
+
+def test_loss_functions_against_reference():
+    """frequency_aware_loss (webp_training.py:105-132) and avif_frequency_aware_loss (avif.py:126-164) executed verbatim from the
+    reference, with pytorch_msssim.ssim (absent here) replaced by the oracle's restatement: pins every other term of the oracle."""
+    g = torch.Generator().manual_seed(4)
+    target = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    pred = target + 0.2 * torch.randn(2, 3, 32, 32, generator=g)
+    stand_in = lambda a, b, data_range=1.0, size_average=True: R.ssim(a, b, data_range)
+    ref_a = rl.load_avif_loss(stand_in)["avif_frequency_aware_loss"](pred, target)
+    assert abs(float(ref_a) - float(R.avif_frequency_aware_loss(pred, target))) < 1e-6 * abs(float(ref_a))
+    ref_w = rl.load_webp_loss(stand_in)["frequency_aware_loss"](pred, target)
+    assert abs(float(ref_w) - float(R.frequency_aware_loss(pred, target))) < 1e-6 * abs(float(ref_w))
