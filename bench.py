@@ -14,6 +14,7 @@ Weak scaling: every rank restores its own batch of 64 images (images are indepen
 data path; torch.distributed is used only for the barrier and the max-over-ranks time).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -181,19 +182,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_train(args):
+def train_line(args, dev, rank, world, steps=None):
     """BASELINE configs[3]: webp_training.py training step, bf16 operands, batch 256 sharded over 8 GPUs (32 per GPU,
-    weak scaling), one NCCL all-reduce of the flat fp32 gradient per step.  Secondary line (not the headline metric)."""
+    weak scaling), NCCL all-reduce of the flat fp32 gradient in buckets under the backward.  Needs the process group of a
+    multi-rank run to exist already; every rank must call it.  Returns the line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     import ddpm_image_restoration_b200 as P
     from ddpm_image_restoration_b200 import codec, ops
     from ddpm_image_restoration_b200.training import Trainer
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     Bn, res = (args.batch if args.batch != 64 else 32), (args.res if args.res != 256 else 64)
     torch.manual_seed(0)
     model = P.WebPDiffusionModel().to(dev).set_precision("bf16")
@@ -203,7 +200,7 @@ def run_train(args):
     xt = codec.webp_compress(x0, 30).contiguous().pin_memory()
     x0 = x0.pin_memory()
     t = (torch.randint(1, 100, (Bn,), generator=g).float() / 100.0).pin_memory()
-    K = args.steps if args.steps is not None else 10
+    K = steps if steps is not None else 10
     Wm = max(3, args.warmup)
 
     def one():
@@ -214,8 +211,8 @@ def run_train(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ops.LAUNCHES[0] = 0
-    clocks = ClockSampler(local); clocks.start()
+    launches0 = ops.LAUNCHES[0]
+    clocks = ClockSampler(dev.index); clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
@@ -237,18 +234,34 @@ def run_train(args):
         hi, lo = chk.clone(), chk.clone()
         dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         sync_err = float((hi - lo) / hi)
+    if rank != 0:
+        return None
+    val = world * Bn * K / (ms / 1e3)
+    nparam = sum(p.numel() for p in model.parameters())
+    return {"metric": "training images/sec (webp_training.py step, 64^2)", "value": val, "unit": "images/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"webp_training.py training step, WebP UNet {res}x{res}, batch {Bn}/GPU, "
+                                   "frequency_aware_loss, clip+AdamW, fp32 gradient all-reduce (NCCL) in " + ("one piece after" if args.no_overlap else "buckets under") + " the backward",
+                       "allreduce_bytes": nparam * 4, "allreduce_collectives_per_step": tr.buckets.collectives / (K + Wm)},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 2 * xt.numel() * 4 + Bn * 4,
+                    "d2h_bytes_per_step": 4.0 / K},
+            "gpu_launches": ops.LAUNCHES[0] - launches0, "clocks": clk, "loss": lossv, "replica_param_mismatch": sync_err}
+
+
+def run_train(args):
+    """`--workload train`: the training line on its own (secondary metric; the default run folds the same line into
+    `secondary` at every N, so the driver's 1/2/4/8-GPU records carry the data-parallel training step too)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = train_line(args, dev, rank, world, args.steps)
     if rank == 0:
-        val = world * Bn * K / (ms / 1e3)
-        nparam = sum(p.numel() for p in model.parameters())
-        print(json.dumps({"metric": "training images/sec (webp_training.py step, 64^2)", "value": val, "unit": "images/s", "n_gpus": world,
-                          "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                          "config": {"workload": f"webp_training.py training step, WebP UNet {res}x{res}, batch {Bn}/GPU, "
-                                                 "frequency_aware_loss, clip+AdamW, fp32 gradient all-reduce (NCCL) in " + ("one piece after" if args.no_overlap else "buckets under") + " the backward",
-                                     "allreduce_bytes": nparam * 4},
-                          "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 2 * xt.numel() * 4 + Bn * 4,
-                                  "d2h_bytes_per_step": 4.0 / K},
-                          "gpu_launches": ops.LAUNCHES[0], "clocks": clk, "loss": lossv, "replica_param_mismatch": sync_err}), flush=True)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -257,8 +270,11 @@ def run_train(args):
 def op_work(name, tag):
     """-> ("flops" | "bytes", amount) of one call: the ALGORITHMIC work, not what the kernel moves."""
     if name in ("conv3x3", "gemm"):
-        B, H, W, K, N = tag
+        B, H, W, K, N, io = tag
         return "flops", 2.0 * B * H * W * K * N * (9 if name == "conv3x3" else 1)
+    if name.startswith("igemm_tc_stream_kernel"):
+        B, H, W = tag                                               # amount is summed per call by summarize_ops
+        return "bytes", 0.0
     if name == "attention":
         B, L, C, heads = tag
         return "flops", 4.0 * B * float(L) * L * C                 # QK^T + PV of the reference's softmax attention
@@ -301,16 +317,35 @@ def op_work(name, tag):
     return "bytes", 0.0
 
 
+def igemm_stream_kernel(name, tag, num_sms=148):
+    """Name of the persistent weight-resident kernel a conv3x3/gemm call of this shape runs on, or None for the tiled kernel
+    (mirror of the dispatch rule in csrc/conv_tc.cu: ddpmir_igemm_tc -- whole weight in shared memory, >= 2 pixel tiles per SM)."""
+    B, H, W, K, N, io = tag
+    taps = 9 if name == "conv3x3" else 1
+    if N % 16 or N > 256 or N * taps * K * 2 > 112 * 1024 or -(-B * H * W // 128) < 2 * num_sms:
+        return None
+    return f"igemm_tc_stream_kernel<{128 if N <= 64 else 256 if N <= 128 else 512}>"
+
+
 def summarize_ops(timed, pk):
-    """{class: {...}} of one profiled step + the list of (op, shape) groups, largest first."""
+    """{class: {...}} of one profiled step + the list of groups, largest first.  A group is an (op, shape) pair, except that
+    every conv3x3/gemm call that runs on the persistent streaming kernel is grouped by KERNEL and activation extent: those
+    layers (K <= 576, N <= 256 over >= 296 pixel tiles) are bound by moving their operands, so the group's work is the
+    algorithmic BYTES of its calls (operand in, every output / residual / gate tensor once), not their FLOP."""
     classes, groups = {}, {}
     for name, lst in timed.items():
         for ms, tag in lst:
             kind, amount = op_work(name, tag)
             c = classes.setdefault(name, {"ms": 0.0, "calls": 0, "kind": kind, "work": 0.0})
             c["ms"] += ms; c["calls"] += 1; c["work"] += amount
-            g = groups.setdefault((name, tag), {"ms": 0.0, "calls": 0, "kind": kind, "work": 0.0})
-            g["ms"] += ms; g["calls"] += 1; g["work"] += amount
+            gkey, gkind, gamount = (name, tag), kind, amount
+            if name in ("conv3x3", "gemm"):
+                kern = igemm_stream_kernel(name, tag)
+                if kern:
+                    gkey, gkind, gamount = (kern, tag[:3]), "bytes", float(tag[0] * tag[1] * tag[2] * tag[5])
+            g = groups.setdefault(gkey, {"ms": 0.0, "calls": 0, "kind": gkind, "work": 0.0})
+            g["ms"] += ms; g["calls"] += 1; g["work"] += gamount
+            g["work_total"] = g["work"]
     for c in list(classes.values()) + list(groups.values()):
         rate = c["work"] / max(c["ms"], 1e-9) * 1e3
         if c["kind"] == "flops":
@@ -622,7 +657,7 @@ def main():
         step_ms, timed, tiers = profile_one_step(job, lambda: torch.cuda.synchronize())
         classes, groups = summarize_ops(timed, pk)
         conv_ms = sum(classes[n]["ms"] for n in ("conv3x3", "gemm") if n in classes)
-        conv_fl = sum(g_["tflops"] * g_["ms"] for (n, _), g_ in groups if n in ("conv3x3", "gemm"))   # TFLOP/s * ms = GFLOP
+        conv_fl = sum(classes[n]["tflops"] * classes[n]["ms"] for n in ("conv3x3", "gemm") if n in classes)   # TFLOP/s * ms = GFLOP
         if conv_ms > 0:
             roof_convs = {"bound": "tensor", "kernel": "igemm_tc_kernel / igemm_tc_stream_kernel (every conv3x3 and 1x1 GEMM of one timestep)",
                           "achieved": conv_fl / conv_ms, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -645,6 +680,8 @@ def main():
         traffic, tsrc = traffic_from_profile(key)
         kind, work = op_work(dname, dtag)
         avg_ms = dg["ms"] / dg["calls"]
+        if dname.startswith("igemm_tc_stream_kernel"):
+            work = dg["work_total"] / dg["calls"]            # mean algorithmic bytes per launch of this kernel in the step
         if dname == "attention":
             # executed tensor-core arithmetic of exactly these calls (their verdicts), not the reference's 4 L^2 C
             mine = [t_ for t_ in tiers if (t_[0], t_[1], t_[2], t_[3]) == tuple(dtag)]
@@ -661,6 +698,12 @@ def main():
         roof.update({"kernel": key, "launch_ms": avg_ms, "launches_per_step": dg["calls"], "share_of_step": dg["ms"] / step_ms,
                      "traffic": traffic, "traffic_source": tsrc, "algorithmic_work": work,
                      "profiled_step_ms": step_ms})
+        if dname.startswith("igemm_tc_stream_kernel"):
+            roof["note"] = ("persistent weight-resident tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu) over every conv3x3 / 1x1 GEMM of "
+                            "the full-resolution levels that it serves (the launches differ in K, N and epilogue tensors): achieved = "
+                            "sum of their algorithmic bytes (bf16 operand in + each output / residual / gate tensor once) / sum of "
+                            "their times; launch_ms and algorithmic_work are per-launch means.  The tensor-roofline view of all "
+                            "convs is roofline_convs; the attention calls are roofline_attention")
         if dname == "attention":
             roof["reference_equivalent_tflops"] = op_work(dname, dtag)[1] / (avg_ms * 1e-3) / 1e12
             roof["note"] = ("one attention call of the full-resolution blocks = pre-pass + polynomial-kernel tier (attn_lin_tc.cu: "
@@ -706,6 +749,32 @@ def main():
             "launch_host_ms_per_step": sum(s_["enqueue_s"] for s_ in stats_f) * 1e3 / K,
             "wall_ms_per_step": sum(wall_f), "finite": all(s_["finite"] for s_ in stats_f), "secondary": secondary,
         }
+    else:
+        line = None
+    if args.secondary and args.family == "avif" and args.res == 256 and args.batch == 64:
+        # BASELINE configs[3] (data-parallel training step) at THIS run's N, so the 1/2/4/8-GPU records carry the gradient
+        # all-reduce over NVLink too.  Every rank takes part; a watchdog prints the headline without it if a rank gets stuck.
+        import threading
+        TRAIN_KEY = "config4_train_webp64_b32_per_gpu"
+
+        def give_up():
+            if rank == 0:
+                line["secondary"] = dict(line["secondary"] or {}, **{TRAIN_KEY: {"error": "timed out after 240 s"}})
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(240.0, give_up); dog.daemon = True; dog.start()
+        del jobs, job
+        gc.collect(); torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        try:
+            tl = train_line(args, dev, rank, world)
+        except Exception as e:                      # a secondary line must never take the headline down
+            tl = {"error": f"{type(e).__name__}: {e}"}
+        dog.cancel()
+        if rank == 0:
+            tl["bench_wall_s"] = time.perf_counter() - t0
+            line["secondary"] = dict(line["secondary"] or {}, **{TRAIN_KEY: tl})
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -71,6 +71,11 @@ _SIGNATURES = {
     "ddpmir_groupnorm_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
     "ddpmir_gate_backward": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_lrelu_mask_backward": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "ddpmir_avif_combine_backward": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "ddpmir_avif_gates_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_avgpool_pyramid_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "ddpmir_block_transform_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_relu_mask_backward": (c_int, [_P, _P, c_int, _P, c_int64, _P]),
     "ddpmir_dropout": (c_int, [_P, c_int, _P, c_int, c_int64, c_float, c_uint64, _P]),
     "ddpmir_maxpool2_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "ddpmir_upsample2_concat_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

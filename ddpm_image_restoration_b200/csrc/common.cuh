@@ -120,3 +120,25 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// ---- geometry shared by the AVIF gate kernels (forward: spatial.cu, backward: backward_avif.cu) ----------------------------
+// cell index of the [85, B, C] pyramid (s = 1, 2, 4, 8 -> bases 0, 1, 5, 21) -> scale and cell coordinates
+__device__ __forceinline__ void pyramid_cell(int cell, int& s, int& ci, int& cj) {
+    int base;
+    if (cell < 1) { s = 1; base = 0; }
+    else if (cell < 5) { s = 2; base = 1; }
+    else if (cell < 21) { s = 4; base = 5; }
+    else { s = 8; base = 21; }
+    const int k = cell - base;
+    ci = k / s; cj = k % s;
+}
+
+__device__ __forceinline__ void bilin_src(int d, int n_in, int n_out, int& i0, int& i1, float& lam) {
+    // F.interpolate(size=...), mode='bilinear', align_corners=False: scale = n_in / n_out
+    float s = ((float)d + 0.5f) * ((float)n_in / (float)n_out) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    lam = s - (float)i0;
+}

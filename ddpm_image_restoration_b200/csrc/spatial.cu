@@ -131,16 +131,6 @@ upsample2_concat_kernel(const T* __restrict__ lo, const T* __restrict__ skip, T*
 // ---- adaptive average pool pyramid (s = 1, 2, 4, 8) ------------------------------------------------------
 // generic adaptive pooling: cell i of s covers [floor(i*n/s), ceil((i+1)*n/s)).  One CTA per (cell, b);
 // threads stride channels (coalesced) and split the window rows between y-lanes.
-__device__ __forceinline__ void pyramid_cell(int cell, int& s, int& ci, int& cj) {
-    int base;
-    if (cell < 1) { s = 1; base = 0; }
-    else if (cell < 5) { s = 2; base = 1; }
-    else if (cell < 21) { s = 4; base = 5; }
-    else { s = 8; base = 21; }
-    const int k = cell - base;
-    ci = k / s; cj = k % s;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 avgpool_pyramid_kernel(const T* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C, int cell_lo) {
@@ -195,16 +185,6 @@ __global__ void avgpool_coarsen_kernel(float* __restrict__ out, int C, int B) {
 }
 
 // ---- AVIF combine ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void bilin_src(int d, int n_in, int n_out, int& i0, int& i1, float& lam) {
-    // F.interpolate(size=...), mode='bilinear', align_corners=False: scale = n_in / n_out
-    float s = ((float)d + 0.5f) * ((float)n_in / (float)n_out) - 0.5f;
-    s = s < 0.f ? 0.f : s;
-    i0 = (int)s;
-    if (i0 > n_in - 1) i0 = n_in - 1;
-    i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
-    lam = s - (float)i0;
-}
-
 template <typename TH, typename T>
 __global__ void __launch_bounds__(256)
 avif_combine_kernel(const TH* __restrict__ hsrc, const T* __restrict__ xt, const float* __restrict__ gates,

@@ -364,7 +364,9 @@ def _igemm(kind, x, w, N, impl, out_dtype, out2_dtype, epi):
     out2 = torch.empty((B, H, W, N), dtype=out2_dtype, device=x.device) if out2_dtype is not None else None
     e = _epi(out_dtype, out2, **epi)
     fn = _lib.lib().ddpmir_conv3x3 if taps == 9 else _lib.lib().ddpmir_gemm
-    with _timed(kind, (B, H, W, K, N), 1):
+    # bytes per output pixel this call has to move at the least: operand row in, every output/epilogue tensor once
+    io = K * x.element_size() + N * sum(t.element_size() for t in (out, out2, epi.get("mul"), epi.get("res")) if t is not None)
+    with _timed(kind, (B, H, W, K, N, io), 1):
         _lib.check(fn(_p(x), _code(x.dtype), B, H, W, K, _p(w), N, ctypes.byref(e), _p(out), impl, _stream()), kind)
     return out if out2 is None else (out, out2)
 

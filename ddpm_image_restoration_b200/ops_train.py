@@ -62,6 +62,51 @@ def lrelu_mask_backward(dg1, g1, bs, low):
     return dpre
 
 
+def avif_combine_backward(de, xt, gates, color, edge, boost_color, boost_edge):
+    """Product rule of e = h + xt * A * color * edge (ops.avif_combine): -> dxt, dz_color, dz_edge (pre-sigmoid), dattn."""
+    B, H, W, C = de.shape
+    outs = [torch.empty_like(de) for _ in range(4)]
+    _lib.check(_lib.lib().ddpmir_avif_combine_backward(_p(_f32(de, "de")), _p(xt), _p(_f32(gates, "gates")), _p(color), _p(edge),
+                                                       _code(xt.dtype), _p(boost_color), _p(boost_edge), B, H, W, C,
+                                                       *[_p(o) for o in outs], _stream()), "avif_combine_backward")
+    LAUNCHES[0] += 1
+    return outs
+
+
+def avif_gates_backward(dattn):
+    """Transposed bilinear up-sampling of the gate pyramid: [B,H,W,C] -> [85, B, C]."""
+    B, H, W, C = dattn.shape
+    dg = torch.empty((85, B, C), dtype=F32, device=dattn.device)
+    _lib.check(_lib.lib().ddpmir_avif_gates_backward(_p(_f32(dattn, "dattn")), B, H, W, C, _p(dg), _stream()), "avif_gates_backward")
+    LAUNCHES[0] += 1
+    return dg
+
+
+def avgpool_pyramid_backward(dpooled, dx):
+    """dx += transposed adaptive average pooling of dpooled [85, B, C]."""
+    B, H, W, C = dx.shape
+    _lib.check(_lib.lib().ddpmir_avgpool_pyramid_backward(_p(_f32(dpooled, "dpooled")), B, H, W, C, _p(_f32(dx, "dx")), 1, _stream()),
+               "avgpool_pyramid_backward")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def block_transform_wgrad(x, dz, Tm, dT):
+    """dT += weight gradient of the learned per-channel 8x8 transform Z = T X T^T."""
+    B, H, W, C = x.shape
+    _lib.check(_lib.lib().ddpmir_block_transform_wgrad(_p(_f32(x, "x")), _p(_f32(dz, "dz")), _p(_f32(Tm, "T")), Tm.shape[-1], B, H, W, C,
+                                                       _p(_f32(dT, "dT")), _stream()), "block_transform_wgrad")
+    LAUNCHES[0] += 1
+
+
+def relu_mask_backward(dy, y):
+    dpre = torch.empty_like(dy)
+    _lib.check(_lib.lib().ddpmir_relu_mask_backward(_p(_f32(dy, "dy")), _p(y), _code(y.dtype), _p(dpre), dy.numel(), _stream()),
+               "relu_mask_backward")
+    LAUNCHES[0] += 1
+    return dpre
+
+
 def dropout(x, p, seed, out_dtype=None):
     out = torch.empty(x.shape, dtype=x.dtype if out_dtype is None else out_dtype, device=x.device)
     _lib.check(_lib.lib().ddpmir_dropout(_p(x), _code(x.dtype), _p(out), _code(out.dtype), x.numel(), float(p), int(seed), _stream()),
@@ -122,8 +167,11 @@ def time_features(t, dim=256):
     return out
 
 
-def act_forward(x, act):
-    out = torch.empty_like(x)
+def act_forward(x, act, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.numel() != x.numel() or out.dtype != F32 or not out.is_contiguous():
+        raise _lib.DdpmirError("act_forward: bad out tensor")
     _lib.check(_lib.lib().ddpmir_act_forward(_p(_f32(x, "x")), act, _p(out), x.numel(), _stream()), "act_forward")
     LAUNCHES[0] += 1
     return out

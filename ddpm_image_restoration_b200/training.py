@@ -9,7 +9,8 @@ hand-written backward kernels (csrc/backward*.cu, attn_simt.cu, loss.cu, fft.cu)
 tensor.  All gradients live in ONE flat fp32 buffer (parameters' gradients are views into it), so data-parallel training
 is a single NCCL all-reduce of that buffer over NVLink (the only collective of the whole design).
 
-Supported model families: WebP and JPEG (the DCT frequency block); the AVIF family's extra operators have no backward yet.
+Model families: WebP / JPEG (DCT frequency block) and AVIF (`train_epoch_ddrm_avif`, avif.py:528-590: learned per-channel
+transform, multi-scale / colour / edge gates -- csrc/backward_avif.cu -- 8 heads, avif_frequency_aware_loss, AdamW lr 1.5e-4).
 """
 import math
 
@@ -36,10 +37,12 @@ def grad_span_starts(model):
 
 
 class Trainer:
-    def __init__(self, model, lr=2e-4, weight_decay=1e-5, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=1.0, dropout=0.1,
+    def __init__(self, model, lr=None, weight_decay=1e-5, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=1.0, dropout=0.1,
                  seed=0, overlap_allreduce=True, bucket_bytes=64 << 20, scheduler="cosine_warm_restarts"):
-        if model.family not in ("webp", "jpeg"):
-            raise NotImplementedError("training kernels cover the WebP/JPEG families (DCT frequency block) only")
+        if model.family not in ("webp", "jpeg", "avif"):
+            raise NotImplementedError(f"no training kernels for the {model.family!r} family")
+        if lr is None:          # webp_training.py:775 (2e-4); avif.py:796 (1.5e-4)
+            lr = 1.5e-4 if model.family == "avif" else 2e-4
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.max_grad_norm, self.dropout_p, self.seed = max_grad_norm, dropout, seed
@@ -48,6 +51,9 @@ class Trainer:
         if dev.type != "cuda":
             raise RuntimeError("training runs on CUDA only (no CPU fallback)")
         self.params = {k: p for k, p in model.named_parameters()}
+        # AVIFAdaptiveTransform.inverse_weights is registered but never used in forward (avif.py:192): torch leaves its .grad
+        # None, so clip_grad_norm_ and AdamW (weight decay included) skip it -- so does optimizer_step below
+        self.unused = {k for k in self.params if k.endswith(".inverse_weights")}
         n = sum(p.numel() for p in self.params.values())
         self.flat_grad = torch.zeros((n,), dtype=F32, device=dev)
         self.grads, off = {}, 0
@@ -85,6 +91,7 @@ class Trainer:
         l1 = lambda w: cast(w.reshape(w.shape[0], -1))
         l1t = lambda w: cast(w.reshape(w.shape[0], -1).t())
         P = {}
+        avif = m.family == "avif"
         for p, ci, co in _BLOCKS:
             q = {}
             if ci != 3:
@@ -95,13 +102,28 @@ class Trainer:
             q["in"], q["in_t"] = l1(sd[f"{p}.attn.in_proj_weight"]), l1t(sd[f"{p}.attn.in_proj_weight"])
             q["out"], q["out_t"] = l1(sd[f"{p}.attn.out_proj.weight"]), l1t(sd[f"{p}.attn.out_proj.weight"])
             f = f"{p}.freq_guide"
-            w1 = torch.cat([sd[f"{f}.low_freq_attn.0.weight"], sd[f"{f}.high_freq_attn.0.weight"]], 0).reshape(co, co)
-            w2 = torch.cat([sd[f"{f}.low_freq_attn.2.weight"].reshape(co, co // 2), sd[f"{f}.high_freq_attn.2.weight"].reshape(co, co // 2)], 1)
-            q["g1"], q["g1_t"] = cast(w1), cast(w1.t())
-            q["g2"], q["g2_t"] = cast(w2), cast(w2.t())
-            q["g1_b"] = torch.cat([sd[f"{f}.low_freq_attn.0.bias"], sd[f"{f}.high_freq_attn.0.bias"]], 0).contiguous().float()
+            if avif:
+                a = f"{f}.adaptive_transform"
+                for key, name in (("q0", f"{a}.quantization.0"), ("q2", f"{a}.quantization.2"),
+                                  ("c0", f"{f}.color_consistency.0"), ("c2", f"{f}.color_consistency.2")):
+                    q[key], q[key + "_t"] = l1(sd[name + ".weight"]), l1t(sd[name + ".weight"])
+                for key, name in (("e0", f"{f}.edge_preserve.0"), ("e2", f"{f}.edge_preserve.2")):
+                    q[key], q[key + "_t"] = c3(sd[name + ".weight"]), c3t(sd[name + ".weight"])
+                q["Tt"] = sd[f"{a}.transform_weights"].transpose(1, 2).contiguous().float()
+            else:
+                w1 = torch.cat([sd[f"{f}.low_freq_attn.0.weight"], sd[f"{f}.high_freq_attn.0.weight"]], 0).reshape(co, co)
+                w2 = torch.cat([sd[f"{f}.low_freq_attn.2.weight"].reshape(co, co // 2), sd[f"{f}.high_freq_attn.2.weight"].reshape(co, co // 2)], 1)
+                q["g1"], q["g1_t"] = cast(w1), cast(w1.t())
+                q["g2"], q["g2_t"] = cast(w2), cast(w2.t())
+                q["g1_b"] = torch.cat([sd[f"{f}.low_freq_attn.0.bias"], sd[f"{f}.high_freq_attn.0.bias"]], 0).contiguous().float()
             q["fo"], q["fo_t"] = c3(sd[f"{f}.conv_out.weight"]), c3t(sd[f"{f}.conv_out.weight"])
             P[p] = q
+        if avif:
+            q = {}
+            for key, name in (("q0", "avif_layer.quantization.0"), ("q2", "avif_layer.quantization.2")):
+                q[key], q[key + "_t"] = l1(sd[name + ".weight"]), l1t(sd[name + ".weight"])
+            q["Tt"] = sd["avif_layer.transform_weights"].transpose(1, 2).contiguous().float()
+            P["tail"] = q
         return P, dt
 
     def _op(self, x, dt):
@@ -141,7 +163,11 @@ class Trainer:
             u1 = ops.linear_rows(feat, sd["time_embed.proj.0.weight"], sd["time_embed.proj.0.bias"])
             hmid = T.act_forward(u1, ops.ACT_SILU)
             t_emb = ops.linear_rows(hmid, sd["time_embed.proj.2.weight"], sd["time_embed.proj.2.bias"])
-            boost = torch.clamp(1.0 - t, fam["clamp"][0], fam["clamp"][1]).contiguous()
+            avif = m.family == "avif"
+            if avif:      # colour / edge boosts of AVIFFreqAwareBlock (avif.py:309-310); compression_level = t (avif.py:566)
+                boost = (torch.clamp(0.5 + 0.5 * (1.0 - t), 0.3, 1.5).contiguous(), torch.clamp(0.7 + 0.3 * (1.0 - t), 0.5, 1.3).contiguous())
+            else:
+                boost = torch.clamp(1.0 - t, fam["clamp"][0], fam["clamp"][1]).contiguous()
             tapes = {}
 
             def blk(p, z, idx):
@@ -161,21 +187,29 @@ class Trainer:
             u3 = blk("up3", ops.upsample2_concat(u2, d3), 10)
             u4 = blk("up4", ops.upsample2_concat(u3, d2), 11)
             u5 = blk("up5", ops.upsample2_concat(u4, d1), 12)
-            Dm = sd["dct_layer.dct_matrix"]
-            comb = ops.block_transform(u5, Dm, 1.0, fam["tail"])
+            if avif:      # u5 + 0.15 * avif_layer(u5), avif_inference.py:383
+                tailv = torch.full((B,), fam["tail"], dtype=F32, device=xt.device)
+                comb, tail_tape = self._tgate_fwd("avif_layer", u5, sd, P["tail"], dt, impl, scale=tailv, res=u5)
+            else:
+                Dm = sd["dct_layer.dct_matrix"]
+                comb = ops.block_transform(u5, Dm, 1.0, fam["tail"])
             st_t = ops.groupnorm_stats(comb, 8)
             a_t = ops.groupnorm_apply(comb, st_t, sd["out_conv.0.weight"], sd["out_conv.0.bias"], ops.ACT_SILU, out_dtype=dt)
             pred = ops.out_conv_tanh(a_t, sd["out_conv.2.weight"], sd["out_conv.2.bias"])
-            recon = ops.lincomb(xt, 1.0, pred, 1.0)                       # xt + pred, webp_training.py:515
-            from .losses import frequency_aware_loss
-            loss = frequency_aware_loss(recon, x0)
+            recon = ops.lincomb(xt, 1.0, pred, 1.0)                       # xt + pred, webp_training.py:515 / avif.py:570
+            from . import losses
+            loss = (losses.avif_frequency_aware_loss if avif else losses.frequency_aware_loss)(recon, x0)
 
             # ---------------- backward ----------------
-            dpred = T.frequency_aware_loss_backward(recon, x0)
+            dpred = (T.avif_frequency_aware_loss_backward if avif else T.frequency_aware_loss_backward)(recon, x0)
             da = T.out_conv_tanh_backward(a_t, pred, dpred, sd["out_conv.2.weight"], G["out_conv.2.weight"], G["out_conv.2.bias"])
             dcomb = T.groupnorm_backward(comb, da, st_t, sd["out_conv.0.weight"], sd["out_conv.0.bias"], ops.ACT_SILU,
                                          G["out_conv.0.weight"], G["out_conv.0.bias"])
-            du5 = ops.block_transform(dcomb, Dm.t().contiguous(), 1.0, fam["tail"])
+            if avif:
+                dxt_tail = ops.lincomb(dcomb, fam["tail"])
+                du5 = self._tgate_bwd("avif_layer", dxt_tail, tail_tape, sd, P["tail"], dt, impl, res=dcomb)
+            else:
+                du5 = ops.block_transform(dcomb, Dm.t().contiguous(), 1.0, fam["tail"])
             dt_emb = torch.zeros_like(t_emb)
 
             def bwd(p, dout):
@@ -248,24 +282,134 @@ class Trainer:
         qkv = ops.gemm(h2_op, W["in"], 3 * co, impl, bias=sd[f"{p}.attn.in_proj_bias"])
         ao, lse = T.attention_train_forward(qkv.view(Bn, H * Wd, 3 * co), fam["heads"])
         ao = ao.view(Bn, H, Wd, co)
-        h3 = ops.gemm(ao, W["out"], co, impl, out_dtype=F32, bias=sd[f"{p}.attn.out_proj.bias"], res=h2)
         f = f"{p}.freq_guide"
-        d = ops.block_transform(h3, sd[f"{f}.dct.dct_matrix"], 0.0, 1.0, out_dtype=dt)
-        g1 = ops.gemm(d, W["g1"], co, impl, bias=W["g1_b"], act=ops.ACT_LRELU02, freq_mode=1, bs=fam["bs"], low=fam["low"])
-        # gate values g = sigmoid(z) kept for the backward (the inference path fuses g*s*d + h3 into this epilogue)
-        g = ops.gemm(g1, W["g2"], co, impl, bias=sd[f"{f}.low_freq_attn.2.bias"], bias2=sd[f"{f}.high_freq_attn.2.bias"],
-                     act=ops.ACT_SIGMOID, freq_mode=2, bs=fam["bs"], low=fam["low"])
-        e = ops.gemm(g1, W["g2"], co, impl, bias=sd[f"{f}.low_freq_attn.2.bias"], bias2=sd[f"{f}.high_freq_attn.2.bias"],
-                     act=ops.ACT_SIGMOID, freq_mode=2, bs=fam["bs"], low=fam["low"], img_scale=boost, mul=d, res=h3)
+        if self.model.family == "avif":
+            h3, h3_op = ops.gemm(ao, W["out"], co, impl, out_dtype=F32, out2_dtype=dt, bias=sd[f"{p}.attn.out_proj.bias"], res=h2)
+            e = self._avif_freq_fwd(f, h3, h3_op, boost, sd, W, dt, impl, tp)
+        else:
+            h3 = ops.gemm(ao, W["out"], co, impl, out_dtype=F32, bias=sd[f"{p}.attn.out_proj.bias"], res=h2)
+            d = ops.block_transform(h3, sd[f"{f}.dct.dct_matrix"], 0.0, 1.0, out_dtype=dt)
+            g1 = ops.gemm(d, W["g1"], co, impl, bias=W["g1_b"], act=ops.ACT_LRELU02, freq_mode=1, bs=fam["bs"], low=fam["low"])
+            # gate values g = sigmoid(z) kept for the backward (the inference path fuses g*s*d + h3 into this epilogue)
+            g = ops.gemm(g1, W["g2"], co, impl, bias=sd[f"{f}.low_freq_attn.2.bias"], bias2=sd[f"{f}.high_freq_attn.2.bias"],
+                         act=ops.ACT_SIGMOID, freq_mode=2, bs=fam["bs"], low=fam["low"])
+            e = ops.gemm(g1, W["g2"], co, impl, bias=sd[f"{f}.low_freq_attn.2.bias"], bias2=sd[f"{f}.high_freq_attn.2.bias"],
+                         act=ops.ACT_SIGMOID, freq_mode=2, bs=fam["bs"], low=fam["low"], img_scale=boost, mul=d, res=h3)
+            tp.update(d=d, g1=g1, g=g)
         out = ops.conv3x3(e, W["fo"], co, impl, out_dtype=F32, bias=sd[f"{f}.conv_out.bias"], res=sc)
-        tp.update(h1=h1, st2=st2, a2d=a2d, dseed=dseed, h2_op=h2_op, qkv=qkv, ao=ao, lse=lse, d=d, g1=g1, g=g, e=e, co=co)
+        tp.update(h1=h1, st2=st2, a2d=a2d, dseed=dseed, h2_op=h2_op, qkv=qkv, ao=ao, lse=lse, e=e, co=co)
         return out, tp
+
+    # ---- AVIF family: learned transform with its sigmoid "quantisation" gate (AVIFAdaptiveTransform, avif.py:185-243) ---------
+    def _tgate_fwd(self, a, x, sd, W, dt, impl, scale=None, res=None):
+        """x (fp32 stream) -> xt = tr * sigmoid(q2(relu(q0(tr)))), tr = T_c X T_c^T;  returns (xt in dt, tape), or with
+        `res` (and a per-image `scale`) the fp32 stream tensor res + scale * xt (the UNet tail, avif_inference.py:383)."""
+        co = x.shape[-1]
+        Tw = sd[f"{a}.transform_weights"]
+        tr = ops.block_transform(x, Tw, 0.0, 1.0, out_dtype=dt)
+        q1 = ops.gemm(tr, W["q0"], co, impl, bias=sd[f"{a}.quantization.0.bias"], act=ops.ACT_RELU)
+        g = ops.gemm(q1, W["q2"], co, impl, bias=sd[f"{a}.quantization.2.bias"], act=ops.ACT_SIGMOID)       # gate kept for the backward
+        xt = ops.gemm(q1, W["q2"], co, impl, out_dtype=None if res is None else F32, bias=sd[f"{a}.quantization.2.bias"],
+                      act=ops.ACT_SIGMOID, img_scale=scale, mul=tr, res=res)
+        return xt, dict(x=x, tr=tr, q1=q1, g=g)
+
+    def _tgate_bwd(self, a, dxt, tp, sd, W, dt, impl, res):
+        """Gradient of _tgate_fwd: parameter gradients into self.grads, returns res + d x."""
+        G = self.grads
+        op = lambda z: self._op(z, dt)
+        co = dxt.shape[-1]
+        ones = self._ones(dxt.shape[0], dxt.device)
+        dz, dtr = T.gate_backward(dxt, tp["g"], tp["tr"], ones, 1, 1)          # xt = g * tr: dz = dxt*tr*g(1-g), dtr = dxt*g
+        dz_op = op(dz)
+        T.wgrad(dz_op, tp["q1"], G[f"{a}.quantization.2.weight"], 1)
+        T.colsum(dz, G[f"{a}.quantization.2.bias"])
+        dq1 = ops.gemm(dz_op, W["q2_t"], co, impl, out_dtype=F32)
+        dpre = T.relu_mask_backward(dq1, tp["q1"])
+        dpre_op = op(dpre)
+        T.wgrad(dpre_op, tp["tr"], G[f"{a}.quantization.0.weight"], 1)
+        T.colsum(dpre, G[f"{a}.quantization.0.bias"])
+        dtr = ops.gemm(dpre_op, W["q0_t"], co, impl, out_dtype=F32, res=dtr)
+        T.block_transform_wgrad(tp["x"], dtr, sd[f"{a}.transform_weights"], G[f"{a}.transform_weights"])
+        return ops.lincomb(res, 1.0, ops.block_transform(dtr, W["Tt"], 0.0, 1.0), 1.0)
+
+    def _ones(self, n, dev):
+        if getattr(self, "_ones_buf", None) is None or self._ones_buf.shape[0] < n:
+            self._ones_buf = torch.ones((max(n, 64),), dtype=F32, device=dev)
+        return self._ones_buf
+
+    def _avif_freq_fwd(self, f, h3, h3_op, boost, sd, W, dt, impl, tp):
+        """AVIFFreqAwareBlock.forward up to `x + enhanced` (avif.py:284-321) with the tape of its backward."""
+        Bn, _, _, co = h3.shape
+        xt, tg = self._tgate_fwd(f"{f}.adaptive_transform", h3, sd, W, dt, impl)
+        pooled = ops.avgpool_pyramid(h3)                       # [85, B, C] fp32: AdaptiveAvgPool2d(1 | 2 | 4 | 8)
+        gates = torch.empty_like(pooled)
+        ms, off = [], 0
+        for i, s in enumerate((1, 2, 4, 8)):
+            rows = pooled[off:off + s * s].reshape(s * s * Bn, co)
+            w1 = sd[f"{f}.multi_scale_attn.{i}.1.weight"].reshape(co // 4, co)
+            w3 = sd[f"{f}.multi_scale_attn.{i}.3.weight"].reshape(co, co // 4)
+            u = ops.linear_rows(rows, w1, sd[f"{f}.multi_scale_attn.{i}.1.bias"])
+            hid = T.act_forward(u, ops.ACT_RELU)
+            z = ops.linear_rows(hid, w3, sd[f"{f}.multi_scale_attn.{i}.3.bias"])
+            T.act_forward(z, ops.ACT_SIGMOID, out=gates[off:off + s * s])
+            ms.append((rows, u, hid, z))
+            off += s * s
+        c1 = ops.gemm(h3_op, W["c0"], co, impl, bias=sd[f"{f}.color_consistency.0.bias"], act=ops.ACT_RELU)
+        color = ops.gemm(c1, W["c2"], co, impl, bias=sd[f"{f}.color_consistency.2.bias"], act=ops.ACT_SIGMOID, img_scale=boost[0])
+        e1 = ops.conv3x3(h3_op, W["e0"], co // 2, impl, bias=sd[f"{f}.edge_preserve.0.bias"], act=ops.ACT_RELU)
+        edge = ops.conv3x3(e1, W["e2"], co, impl, bias=sd[f"{f}.edge_preserve.2.bias"], act=ops.ACT_SIGMOID, img_scale=boost[1])
+        tp.update(tg=tg, xt=xt, gates=gates, ms=ms, h3_op=h3_op, c1=c1, color=color, e1=e1, edge=edge)
+        return ops.avif_combine(h3, xt, gates, color, edge)
+
+    def _avif_freq_bwd(self, f, de, tp, boost, sd, W, dt, impl):
+        """de = gradient at `x + enhanced` -> gradient at the block's h3 (all parameter gradients of the frequency block)."""
+        G = self.grads
+        op = lambda z: self._op(z, dt)
+        Bn, _, _, co = de.shape
+        dxt, dzc, dze, dattn = T.avif_combine_backward(de, tp["xt"], tp["gates"], tp["color"], tp["edge"], boost[0], boost[1])
+        # edge gate: sigmoid(conv3x3(relu(conv3x3(h3))))
+        dze_op = op(dze)
+        T.wgrad(dze_op, tp["e1"], G[f"{f}.edge_preserve.2.weight"], 9, oihw=True)
+        T.colsum(dze, G[f"{f}.edge_preserve.2.bias"])
+        de1 = ops.conv3x3(dze_op, W["e2_t"], co // 2, impl, out_dtype=F32)
+        dpe = T.relu_mask_backward(de1, tp["e1"])
+        dpe_op = op(dpe)
+        T.wgrad(dpe_op, tp["h3_op"], G[f"{f}.edge_preserve.0.weight"], 9, oihw=True)
+        T.colsum(dpe, G[f"{f}.edge_preserve.0.bias"])
+        dh3 = ops.conv3x3(dpe_op, W["e0_t"], co, impl, out_dtype=F32, res=de)        # + the direct path  x + enhanced
+        # colour gate: sigmoid(1x1(relu(1x1(h3))))
+        dzc_op = op(dzc)
+        T.wgrad(dzc_op, tp["c1"], G[f"{f}.color_consistency.2.weight"], 1)
+        T.colsum(dzc, G[f"{f}.color_consistency.2.bias"])
+        dc1 = ops.gemm(dzc_op, W["c2_t"], co, impl, out_dtype=F32)
+        dpc = T.relu_mask_backward(dc1, tp["c1"])
+        dpc_op = op(dpc)
+        T.wgrad(dpc_op, tp["h3_op"], G[f"{f}.color_consistency.0.weight"], 1)
+        T.colsum(dpc, G[f"{f}.color_consistency.0.bias"])
+        dh3 = ops.gemm(dpc_op, W["c0_t"], co, impl, out_dtype=F32, res=dh3)
+        # multi-scale gates: bilinear up-sampling and adaptive pooling transposed, the four small MLPs in between
+        dgates = T.avif_gates_backward(dattn)
+        dpooled = torch.empty_like(dgates)
+        off = 0
+        for i, s in enumerate((1, 2, 4, 8)):
+            rows, u, hid, z = tp["ms"][i]
+            w1 = sd[f"{f}.multi_scale_attn.{i}.1.weight"].reshape(co // 4, co)
+            w3 = sd[f"{f}.multi_scale_attn.{i}.3.weight"].reshape(co, co // 4)
+            dz = T.act_backward(dgates[off:off + s * s].reshape(s * s * Bn, co), z, ops.ACT_SIGMOID)
+            dhid = T.linear_rows_backward(dz, hid, w3, G[f"{f}.multi_scale_attn.{i}.3.weight"], G[f"{f}.multi_scale_attn.{i}.3.bias"])
+            du = T.act_backward(dhid, u, ops.ACT_RELU)
+            T.linear_rows_backward(du, rows, w1, G[f"{f}.multi_scale_attn.{i}.1.weight"], G[f"{f}.multi_scale_attn.{i}.1.bias"],
+                                   dx_accum=dpooled[off:off + s * s].view(s * s * Bn, co).zero_())
+            off += s * s
+        T.avgpool_pyramid_backward(dpooled, dh3)
+        # transform branch
+        return self._tgate_bwd(f"{f}.adaptive_transform", dxt, tp["tg"], sd, W, dt, impl, res=dh3)
 
     def _block_bwd(self, p, dout, tp, t_emb, dt_emb, boost, sd, W, dt, impl, p_drop):
         fam = _FAMILY[self.model.family]
         G = self.grads
         co = tp["co"]
-        bs, low = fam["bs"], fam["low"]
+        bs, low = fam["bs"], fam.get("low", 0)
         f = f"{p}.freq_guide"
         op = lambda z: self._op(z, dt)
         Bn, H, Wd, _ = dout.shape
@@ -275,24 +419,10 @@ class Trainer:
         T.wgrad(dout_op, tp["e"], G[f"{f}.conv_out.weight"], 9, oihw=True)
         T.colsum(dout, G[f"{f}.conv_out.bias"])
         de = ops.conv3x3(dout_op, W["fo_t"], co, impl, out_dtype=F32)
-        # e = h3 + g*s*d
-        dz, dd = T.gate_backward(de, tp["g"], tp["d"], boost, bs, low)
-        dz_op = op(dz)
-        T.wgrad(dz_op, tp["g1"], G[f"{f}.low_freq_attn.2.weight"], 1, k_begin=0, k_count=co // 2, out_ld=co // 2)
-        T.wgrad(dz_op, tp["g1"], G[f"{f}.high_freq_attn.2.weight"], 1, k_begin=co // 2, k_count=co // 2, out_ld=co // 2)
-        T.colsum(dz, G[f"{f}.low_freq_attn.2.bias"], cls=1, bs=bs, low=low)
-        T.colsum(dz, G[f"{f}.high_freq_attn.2.bias"], cls=0, bs=bs, low=low)
-        dg1 = ops.gemm(dz_op, W["g2_t"], co, impl, out_dtype=F32)
-        dpre = T.lrelu_mask_backward(dg1, tp["g1"], bs, low)
-        dpre_op = op(dpre)
-        T.wgrad(dpre_op, tp["d"], G[f"{f}.low_freq_attn.0.weight"], 1, n_begin=0, n_count=co // 2)
-        T.wgrad(dpre_op, tp["d"], G[f"{f}.high_freq_attn.0.weight"], 1, n_begin=co // 2, n_count=co // 2)
-        T.colsum(dpre, G[f"{f}.low_freq_attn.0.bias"], n_begin=0, n_count=co // 2)
-        T.colsum(dpre, G[f"{f}.high_freq_attn.0.bias"], n_begin=co // 2, n_count=co // 2)
-        dd = ops.gemm(dpre_op, W["g1_t"], co, impl, out_dtype=F32, res=dd)
-        # h3 receives de directly and through d = DCT(h3)
-        Dt = sd[f"{f}.dct.dct_matrix"].t().contiguous()
-        dh3 = ops.lincomb(de, 1.0, ops.block_transform(dd, Dt, 0.0, 1.0), 1.0)
+        if self.model.family == "avif":
+            dh3 = self._avif_freq_bwd(f, de, tp, boost, sd, W, dt, impl)
+        else:
+            dh3 = self._dct_freq_bwd(f, de, tp, boost, sd, W, dt, impl, bs, low)
         # h3 = out_proj(ao) + h2
         dh3_op = op(dh3)
         T.wgrad(dh3_op, tp["ao"], G[f"{p}.attn.out_proj.weight"], 1)
@@ -338,6 +468,31 @@ class Trainer:
         return T.groupnorm_backward(tp["x"], da, tp["st1"], sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], ops.ACT_NONE,
                                     G[f"{p}.norm1.weight"], G[f"{p}.norm1.bias"], dx=dx, accumulate=True)
 
+    def _dct_freq_bwd(self, f, de, tp, boost, sd, W, dt, impl, bs, low):
+        """WebP/JPEG frequency block: de = gradient at e = h3 + g*s*d  ->  gradient at h3."""
+        G = self.grads
+        op = lambda z: self._op(z, dt)
+        co = tp["co"]
+        # e = h3 + g*s*d
+        dz, dd = T.gate_backward(de, tp["g"], tp["d"], boost, bs, low)
+        dz_op = op(dz)
+        T.wgrad(dz_op, tp["g1"], G[f"{f}.low_freq_attn.2.weight"], 1, k_begin=0, k_count=co // 2, out_ld=co // 2)
+        T.wgrad(dz_op, tp["g1"], G[f"{f}.high_freq_attn.2.weight"], 1, k_begin=co // 2, k_count=co // 2, out_ld=co // 2)
+        T.colsum(dz, G[f"{f}.low_freq_attn.2.bias"], cls=1, bs=bs, low=low)
+        T.colsum(dz, G[f"{f}.high_freq_attn.2.bias"], cls=0, bs=bs, low=low)
+        dg1 = ops.gemm(dz_op, W["g2_t"], co, impl, out_dtype=F32)
+        dpre = T.lrelu_mask_backward(dg1, tp["g1"], bs, low)
+        dpre_op = op(dpre)
+        T.wgrad(dpre_op, tp["d"], G[f"{f}.low_freq_attn.0.weight"], 1, n_begin=0, n_count=co // 2)
+        T.wgrad(dpre_op, tp["d"], G[f"{f}.high_freq_attn.0.weight"], 1, n_begin=co // 2, n_count=co // 2)
+        T.colsum(dpre, G[f"{f}.low_freq_attn.0.bias"], n_begin=0, n_count=co // 2)
+        T.colsum(dpre, G[f"{f}.high_freq_attn.0.bias"], n_begin=co // 2, n_count=co // 2)
+        dd = ops.gemm(dpre_op, W["g1_t"], co, impl, out_dtype=F32, res=dd)
+        # h3 receives de directly and through d = DCT(h3)
+        Dt = sd[f"{f}.dct.dct_matrix"].t().contiguous()
+        dh3 = ops.lincomb(de, 1.0, ops.block_transform(dd, Dt, 0.0, 1.0), 1.0)
+        return dh3
+
     # ------------------------------------------------------------------------------------------------------------
     def _grads_final_from(self, lo):
         """Called by the backward when every gradient at offsets >= lo is final.  In an overlapped step with several ranks
@@ -359,6 +514,8 @@ class Trainer:
         T.sumsq(self.flat_grad, self._norm_acc)
         b1, b2 = self.betas
         for k, p in self.params.items():
+            if k in self.unused:
+                continue
             T.adamw_step(p.data, self.grads[k], self.m[k], self.v[k], self.lr, b1, b2, self.eps, self.wd, self.step_count,
                          self._norm_acc, self.max_grad_norm)
         self.model._packed = None      # inference weight packs are stale now
@@ -382,3 +539,13 @@ def train_epoch_ddrm_webp(trainer, batches, quality_for_t=None):
         total += float(loss); n += 1
     trainer.scheduler_step()          # scheduler.step() once per epoch, webp_training.py:530
     return total / max(n, 1)
+
+
+def train_epoch_ddrm_avif(trainer, batches):
+    """Loop form of avif.py:528-590 (`train_epoch_ddrm_avif`) over an iterable of (x0, xt, t) device batches: pred =
+    model(xt, t/100, t/100), loss = avif_frequency_aware_loss(xt + pred, x0), clip 1.0, AdamW(lr 1.5e-4, wd 1e-5,
+    betas (0.9, 0.99)), scheduler.step() once per epoch.  The quality schedule and the host AVIF compression of x0
+    (avif.py:539-560) are the caller's data pipeline, as in the reference's loop body."""
+    if trainer.model.family != "avif":
+        raise ValueError("train_epoch_ddrm_avif needs a Trainer over an AVIFDiffusionModel")
+    return train_epoch_ddrm_webp(trainer, batches)

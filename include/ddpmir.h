@@ -349,6 +349,35 @@ int ddpmir_gate_backward(const float* de, const void* g, const void* d, int op_d
 int ddpmir_lrelu_mask_backward(const float* dg1, const void* g1, int op_dtype, float* dpre, int B, int H, int W, int N, int bs,
                                int low, ddpmir_stream_t stream);
 
+/* ---- AVIF family: backward of AVIFFreqAwareBlock / AVIFAdaptiveTransform (avif.py:185-321), used by the training step
+ * train_epoch_ddrm_avif (avif.py:528-590).  GEMM-shaped pieces reuse ddpmir_conv3x3 / ddpmir_gemm / ddpmir_wgrad. ---- */
+
+/* Product rule of e = h + xt * A * color * edge (avif.py:318-321), A = 1/4 sum_s bilinear_up(gates_s) rebuilt from the
+ * [85, B, C] gate pyramid exactly as ddpmir_avif_combine does.  color = boost_color[b] * sigmoid(zc), edge likewise
+ * (avif.py:309-315).  Writes dxt = de*A*color*edge, the PRE-sigmoid gradients dz_color, dz_edge, and dattn = de*xt*color*edge/4
+ * (gradient of the SUM of the up-sampled maps).  xt, color, edge in `dtype`; all outputs fp32 [B,H,W,C]. */
+int ddpmir_avif_combine_backward(const float* de, const void* xt, const float* gates, const void* color, const void* edge,
+                                 int dtype, const float* boost_color, const float* boost_edge, int B, int H, int W, int C,
+                                 float* dxt, float* dz_color, float* dz_edge, float* dattn, ddpmir_stream_t stream);
+
+/* Transposed F.interpolate(bilinear, align_corners=False) of the four gate maps (avif.py:297-300):
+ * dgates[cell, b, c] = sum over pixels of weight(pixel, cell) * dattn[b, pixel, c];  dgates fp32 [85, B, C]. */
+int ddpmir_avif_gates_backward(const float* dattn, int B, int H, int W, int C, float* dgates, ddpmir_stream_t stream);
+
+/* Transposed nn.AdaptiveAvgPool2d(1|2|4|8) (avif.py:197): dx[b,h,w,c] (+)= sum over the cells containing (h,w) of
+ * dpooled[cell,b,c] / |cell|.  dpooled fp32 [85, B, C]; dx fp32 [B,H,W,C], added to when accumulate != 0. */
+int ddpmir_avgpool_pyramid_backward(const float* dpooled, int B, int H, int W, int C, float* dx, int accumulate,
+                                    ddpmir_stream_t stream);
+
+/* Weight gradient of the learned per-channel blockwise transform Z = T_c X T_c^T (AVIFAdaptiveTransform.transform_weights,
+ * avif.py:191,216-223): dT[c] += sum over blocks of dZ^T (T X) + (dZ T) X^T.  x, dz fp32 [B,H,W,C] (zero padding / crop at ragged
+ * edges as in the forward); T, dT fp32 [C, bs, bs]; bs = 8.  The data gradient is ddpmir_block_transform with T_c^T. */
+int ddpmir_block_transform_wgrad(const float* x, const float* dz, const float* T, int bs, int B, int H, int W, int C, float* dT,
+                                 ddpmir_stream_t stream);
+
+/* nn.ReLU backward from the saved OUTPUT y = relu(pre) (y in y_dtype): dpre = dy * [y > 0]. */
+int ddpmir_relu_mask_backward(const float* dy, const void* y, int y_dtype, float* dpre, int64_t n, ddpmir_stream_t stream);
+
 /* nn.Dropout(p) in train mode (webp_inference.py:291,313): out = keep ? in/(1-p) : 0 with a counter-hash mask keyed by
  * (seed, element); applying it to the incoming gradient with the same seed is its backward. */
 int ddpmir_dropout(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, float p, uint64_t seed,

@@ -501,10 +501,12 @@ def avif_frequency_aware_loss(pred: torch.Tensor, target: torch.Tensor) -> torch
 
 
 def training_step_reference(sd: SD, xt, t, x0, family: str = "webp"):
-    """Loss and gradients of one training step (webp_training.py:511-521, dropout disabled) by torch.autograd."""
+    """Loss and gradients of one training step (webp_training.py:511-521 / avif.py:562-573, dropout disabled) by torch.autograd.
+    Parameters the forward never touches (AVIFAdaptiveTransform.inverse_weights) have no gradient and are left out, as
+    torch leaves their .grad None."""
     params = {k: (v.clone().requires_grad_() if v.dtype.is_floating_point and not k.endswith("dct_matrix") else v) for k, v in sd.items()}
     pred = unet_forward(params, xt, t, t.clone(), family, enable_grad=True)
-    loss = frequency_aware_loss(xt + pred, x0)
+    loss = (avif_frequency_aware_loss if family == "avif" else frequency_aware_loss)(xt + pred, x0)     # avif.py:570
     loss.backward()
     return loss.detach(), {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
 

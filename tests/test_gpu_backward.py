@@ -224,6 +224,65 @@ def test_small_layers_backward(ops, T):
     assert rel(nchw(da), a.grad) < 1e-5 and rel(dwo.cpu(), wo.grad) < 1e-5 and rel(dbo.cpu(), bo.grad) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 32, 32), (1, 64, 64, 64), (2, 8, 4, 4), (1, 16, 2, 2), (2, 8, 1, 1), (1, 8, 12, 20), (1, 8, 8, 8)])
+def test_avif_gate_pyramid_backward(ops, T, shape):
+    """e = h + xt * mean_s(up(gate_s)) * color * edge (avif.py:293-321): the product rule, the transposed bilinear up-sampling
+    (incl. s > H, s == H and ragged ratios) and the transposed adaptive pooling, each against torch.autograd."""
+    B, C, H, W = shape
+    h = rnd(B, C, H, W, seed=1)
+    xt = rnd(B, C, H, W, seed=2).requires_grad_()
+    gate_maps = [torch.sigmoid(rnd(B, C, s, s, seed=10 + s)).requires_grad_() for s in (1, 2, 4, 8)]
+    bc, be = torch.tensor([0.9, 1.3][:B]), torch.tensor([0.8, 1.1][:B])
+    zc, ze = rnd(B, C, H, W, seed=3).requires_grad_(), rnd(B, C, H, W, seed=4).requires_grad_()
+    color = torch.sigmoid(zc) * bc.view(-1, 1, 1, 1)
+    edge = torch.sigmoid(ze) * be.view(-1, 1, 1, 1)
+    acc = 0
+    for q in gate_maps:
+        acc = acc + (q if q.shape[-2:] == (H, W) else F.interpolate(q, size=(H, W), mode="bilinear", align_corners=False))
+    e = h + xt * (acc / 4) * color * edge
+    de = rnd(B, C, H, W, seed=5)
+    e.backward(de)
+    gates = torch.cat([q.detach().permute(2, 3, 0, 1).reshape(-1, B, C) for q in gate_maps], 0).contiguous().cuda()
+    fwd = ops.avif_combine(nhwc(h), nhwc(xt.detach()), gates, nhwc(color.detach()), nhwc(edge.detach()))
+    assert rel(nchw(fwd), e.detach()) < 1e-6
+    dxt, dzc, dze, dattn = T.avif_combine_backward(nhwc(de), nhwc(xt.detach()), gates, nhwc(color.detach()), nhwc(edge.detach()),
+                                                   bc.cuda(), be.cuda())
+    assert rel(nchw(dxt), xt.grad) < 1e-5 and rel(nchw(dzc), zc.grad) < 1e-5 and rel(nchw(dze), ze.grad) < 1e-5
+    dg = T.avif_gates_backward(dattn).cpu()
+    want = torch.cat([q.grad.permute(2, 3, 0, 1).reshape(-1, B, C) for q in gate_maps], 0)
+    assert rel(dg, want) < 1e-5
+    # adaptive pooling pyramid, forward and transposed
+    x = rnd(B, C, H, W, seed=6).requires_grad_()
+    pooled = torch.cat([F.adaptive_avg_pool2d(x, s).permute(2, 3, 0, 1).reshape(-1, B, C) for s in (1, 2, 4, 8)], 0)
+    dp = rnd(85, B, C, seed=7)
+    pooled.backward(dp)
+    assert rel(ops.avgpool_pyramid(nhwc(x.detach())).cpu(), pooled.detach()) < 1e-5
+    base = rnd(B, C, H, W, seed=8)
+    dx = T.avgpool_pyramid_backward(dp.cuda(), nhwc(base))
+    assert rel(nchw(dx) - base, x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16), (1, 8, 8, 8), (3, 72, 12, 20), (1, 128, 4, 4)])
+def test_learned_transform_weight_gradient(ops, T, shape):
+    """Z = T_c X T_c^T per channel and 8x8 block (AVIFAdaptiveTransform, avif.py:205-232): dT and dX against autograd over the
+    oracle's block_transform (ragged sizes pad with zeros and crop)."""
+    B, C, H, W = shape
+    x = rnd(B, C, H, W, seed=1).requires_grad_()
+    Tw = (rnd(C, 8, 8, seed=2) * 0.4).requires_grad_()
+    z = R.block_transform(x, Tw)
+    dz = rnd(B, C, H, W, seed=3)
+    z.backward(dz)
+    dT = torch.zeros(C, 8, 8).cuda()
+    T.block_transform_wgrad(nhwc(x.detach()), nhwc(dz), Tw.detach().cuda(), dT)
+    assert rel(dT.cpu(), Tw.grad) < 1e-5
+    dx = ops.block_transform(nhwc(dz), Tw.detach().transpose(1, 2).contiguous().cuda(), 0.0, 1.0)
+    assert rel(nchw(dx), x.grad) < 1e-5
+    y = torch.relu(rnd(2, 8, 8, 16, seed=4))
+    dy = rnd(2, 8, 8, 16, seed=5)
+    for dt in (torch.float32, torch.bfloat16):
+        assert torch.equal(T.relu_mask_backward(dy.cuda(), y.to(dt).cuda()).cpu(), dy * (y > 0))
+
+
 def test_frequency_aware_loss_backward(T):
     gen = g(3)
     target = torch.rand(2, 3, 32, 32, generator=gen) * 2 - 1

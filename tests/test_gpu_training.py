@@ -15,7 +15,7 @@ def make(fam="webp", precision="fp32"):
     import ddpm_image_restoration_b200 as P
     from ddpm_image_restoration_b200.training import Trainer
     sd = W.make_state_dict(fam, 0)
-    m = {"webp": P.WebPDiffusionModel, "jpeg": P.JPEGDiffusionModel}[fam]()
+    m = {"webp": P.WebPDiffusionModel, "jpeg": P.JPEGDiffusionModel, "avif": P.AVIFDiffusionModel}[fam]()
     m.load_state_dict(sd)
     m = m.cuda().set_precision(precision)
     return sd, m, Trainer(m, dropout=0.0)
@@ -28,14 +28,18 @@ def batch(hw=32, b=2):
     return x0, xt, t
 
 
-@pytest.mark.parametrize("fam", ["webp", "jpeg"])
+@pytest.mark.parametrize("fam", ["webp", "jpeg", "avif"])
 def test_gradients_match_autograd_fp32(fam):
     sd, m, tr = make(fam)
     x0, xt, t = batch()
     loss_ref, grads_ref = R.training_step_reference(sd, xt, t, x0, fam)
     loss = tr.forward_backward(xt.cuda(), t.cuda(), x0.cuda())
     assert abs(float(loss) - float(loss_ref)) < 2e-3 * abs(float(loss_ref))
-    assert set(grads_ref) == set(tr.grads)
+    # parameters the forward never uses (AVIF inverse_weights) have no autograd gradient; ours stay exactly zero
+    assert set(grads_ref) == set(tr.grads) - tr.unused
+    assert all(k.endswith("inverse_weights") and not tr.grads[k].any() for k in tr.unused)
+    assert (fam == "avif") == bool(tr.unused)
+    grads_ref = dict(grads_ref, **{k: torch.zeros_like(tr.grads[k]).cpu() for k in tr.unused})
     worst = max((rel(tr.grads[k].cpu(), g), k) for k, g in grads_ref.items())
     flat_ref = torch.cat([grads_ref[k].flatten() for k in tr.grads])
     print(f"{fam}: loss {float(loss):.6f} vs {float(loss_ref):.6f}; global grad rel-L2 {rel(tr.flat_grad.cpu(), flat_ref):.2e}; worst tensor {worst}")
@@ -96,8 +100,46 @@ def test_dropout_changes_the_step_but_is_reproducible():
     assert rel(g1, g2) < 1e-4
 
 
-def test_avif_training_is_refused():
-    import ddpm_image_restoration_b200 as P
-    from ddpm_image_restoration_b200.training import Trainer
-    with pytest.raises(NotImplementedError):
-        Trainer(P.AVIFDiffusionModel().cuda())
+def test_avif_training_step_matches_torch():
+    """train_epoch_ddrm_avif's step (avif.py:562-577): two clip + AdamW(lr 1.5e-4) steps against torch.optim.AdamW fed with the
+    oracle's autograd gradients; inverse_weights (no gradient in torch) must not move, not even by weight decay."""
+    from ddpm_image_restoration_b200.training import train_epoch_ddrm_avif
+    sd, m, tr = make("avif")
+    assert tr.lr == 1.5e-4
+    x0, xt, t = batch()
+    ref = {k: v.clone() for k, v in sd.items()}
+    names = [k for k in tr.params]
+    plist = [ref[k].requires_grad_() for k in names]
+    opt = torch.optim.AdamW(plist, lr=1.5e-4, weight_decay=1e-5, betas=(0.9, 0.99))
+    for step in range(2):
+        cur = {k: v.detach() for k, v in ref.items()}
+        _, grads = R.training_step_reference(cur, xt, t, x0, "avif")
+        for k, p in zip(names, plist):
+            p.grad = grads.get(k)
+        torch.nn.utils.clip_grad_norm_(plist, 1.0)
+        opt.step()
+        if step == 0:
+            tr.train_step(xt.cuda(), t.cuda(), x0.cuda())
+        else:
+            train_epoch_ddrm_avif(tr, [(x0.cuda(), xt.cuda(), (t * 100).cuda())])
+    used = [k for k in names if k not in tr.unused]
+    got = torch.cat([tr.params[k].detach().flatten().cpu() for k in used])
+    want = torch.cat([ref[k].detach().flatten() for k in used])
+    start = torch.cat([sd[k].flatten() for k in used])
+    assert rel(got - start, want - start) < 2e-2
+    for k in tr.unused:
+        assert torch.equal(tr.params[k].detach().cpu(), sd[k])
+    assert tr.lr < 1.5e-4          # the epoch loop stepped the cosine schedule
+
+
+def test_avif_bf16_gradients_are_aligned():
+    sd, m, tr = make("avif", "bf16")
+    x0, xt, t = batch()
+    _, grads_ref = R.training_step_reference(sd, xt, t, x0, "avif")
+    tr.forward_backward(xt.cuda(), t.cuda(), x0.cuda())
+    keys = [k for k in tr.grads if k not in tr.unused]
+    g = torch.cat([tr.grads[k].flatten() for k in keys]).cpu().double()
+    flat_ref = torch.cat([grads_ref[k].flatten() for k in keys]).double()
+    cos = float((g * flat_ref).sum() / (g.norm() * flat_ref.norm()))
+    print(f"avif bf16 gradient cosine vs fp32 autograd: {cos:.5f}, rel-L2 {rel(g, flat_ref):.3e}")
+    assert cos > 0.99
