@@ -749,6 +749,16 @@ def main():
             "launch_host_ms_per_step": sum(s_["enqueue_s"] for s_ in stats_f) * 1e3 / K,
             "wall_ms_per_step": sum(wall_f), "finite": all(s_["finite"] for s_ in stats_f), "secondary": secondary,
         }
+        # what bounds the step: the reference's data-consistency term is a host codec round trip of every image at every
+        # timestep (avif_inference.py:438 / webp_inference.py:581); the pool's thread-time per step / its threads is a floor on
+        # the step no GPU kernel can lower.  gpu_ms_per_step = the libddpmir work of one step (profiled, rank 0).
+        cthreads = max(1, codec.pool_threads())
+        floor = line["codec_cpu_ms_per_step"] / cthreads
+        gpu_ms = roof["profiled_step_ms"] if roof else None
+        line["limiter"] = {"codec_thread_ms_per_step": line["codec_cpu_ms_per_step"], "codec_threads": cthreads,
+                           "host_codec_floor_ms_per_step": floor, "gpu_ms_per_step": gpu_ms,
+                           "bound": "host codec (Pillow round trip mandated by the reference's sampler; scales with host cores per GPU, not with GPUs)"
+                                    if floor > 0.75 * ms_per_step else "gpu"}
     else:
         line = None
     if args.secondary and args.family == "avif" and args.res == 256 and args.batch == 64:
