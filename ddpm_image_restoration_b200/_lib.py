@@ -75,6 +75,7 @@ _SIGNATURES = {
     "ddpmir_avif_gates_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "ddpmir_avgpool_pyramid_backward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "ddpmir_block_transform_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ddpmir_pack_weight": (c_int, [_P, c_int, c_int, c_int, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, _P]),
     "ddpmir_relu_mask_backward": (c_int, [_P, _P, c_int, _P, c_int64, _P]),
     "ddpmir_dropout": (c_int, [_P, c_int, _P, c_int, c_int64, c_float, c_uint64, _P]),
     "ddpmir_maxpool2_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -97,6 +98,7 @@ _SIGNATURES = {
     "ddpmir_huber_backward": (c_int, [_P, _P, c_int64, c_float, c_float, _P, c_int, _P]),
     "ddpmir_color_l1_backward": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P]),
     "ddpmir_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "ddpmir_adamw_multi": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_int, _P, c_float, _P]),
     "ddpmir_adamw_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P, c_float, _P]),
 }
 

@@ -84,34 +84,60 @@ wgrad_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__
 // ---- column sums of dY: bias gradients, per-image row-bias gradients, low/high class-split bias gradients -----------
 // out_total[n] += sum_m sel(m) dY[m,n];  out_img[b,n] += the same per image.  cls: -1 all rows, 0 high-frequency rows
 // only, 1 low-frequency rows only (is_low_freq of the pixel).
+// Threads = CW column lanes (power of two >= n_count, <= 256) x 256 / CW row lanes, four independent partial sums per thread: a
+// 64-column gradient keeps 16 rows in flight per CTA instead of one (the one-row-at-a-time version was latency-bound: 4.2 ms of
+// a 35 ms training step).  Row lanes are folded in shared memory, then one atomic per (column, CTA, image).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ dy, int dtype, long long M, int N, int H, int W, int cls, int bs, int low, int n_begin,
               int n_count, float* __restrict__ out_total, float* __restrict__ out_img, int rows_per_cta) {
+    __shared__ float red[256];
     const int hw = H * W;
     const long long m0 = (long long)blockIdx.x * rows_per_cta;
     const long long m1 = min(M, m0 + rows_per_cta);
     dy = dtype == DDPMIR_F32 ? (const void*)((const float*)dy + n_begin) : (const void*)((const bf16*)dy + n_begin);
     const int ldn = N;
-    N = n_count;
-    for (int n = threadIdx.x; n < N; n += 256) {
-        float s = 0.f;
-        int cur_b = (int)(m0 / hw);
-        for (long long m = m0; m < m1; ++m) {
-            const int b = (int)(m / hw);
-            if (b != cur_b) {
-                if (out_img) atomicAdd(&out_img[(long long)cur_b * N + n], s);
+    int CW = 1;
+    while (CW < n_count && CW < 256) CW <<= 1;
+    const int RL = 256 / CW;
+    const int cn = threadIdx.x & (CW - 1), rl = threadIdx.x / CW;
+    auto take = [&](long long m, int b) -> bool {
+        if (cls < 0) return true;
+        const int rem = (int)(m - (long long)b * hw);
+        const int h = rem / W, w = rem - h * W;
+        return (int)is_low_freq(h, w, H, W, bs, low) == cls;
+    };
+    for (long long seg = m0; seg < m1;) {                      // one segment per image touched by this CTA (usually one)
+        const int b = (int)(seg / hw);
+        const long long seg_end = min(m1, (long long)(b + 1) * hw);
+        for (int nb = 0; nb < n_count; nb += CW) {
+            const int n = nb + cn;
+            float s = 0.f;
+            if (n < n_count) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                long long m = seg + rl;
+                for (; m + 3 * RL < seg_end; m += 4 * RL) {
+                    const float v0 = ld_any(dy, dtype, m * ldn + n), v1 = ld_any(dy, dtype, (m + RL) * ldn + n);
+                    const float v2 = ld_any(dy, dtype, (m + 2 * RL) * ldn + n), v3 = ld_any(dy, dtype, (m + 3 * RL) * ldn + n);
+                    s0 += take(m, b) ? v0 : 0.f; s1 += take(m + RL, b) ? v1 : 0.f;
+                    s2 += take(m + 2 * RL, b) ? v2 : 0.f; s3 += take(m + 3 * RL, b) ? v3 : 0.f;
+                }
+                for (; m < seg_end; m += RL)
+                    if (take(m, b)) s0 += ld_any(dy, dtype, m * ldn + n);
+                s = (s0 + s1) + (s2 + s3);
+            }
+            if (RL > 1) {
+                red[threadIdx.x] = s;
+                __syncthreads();
+                if (rl == 0)
+                    for (int l = 1; l < RL; ++l) s += red[l * CW + cn];
+                __syncthreads();
+            }
+            if (rl == 0 && n < n_count) {
+                if (out_img) atomicAdd(&out_img[(long long)b * n_count + n], s);
                 if (out_total) atomicAdd(&out_total[n], s);
-                s = 0.f; cur_b = b;
             }
-            if (cls >= 0) {
-                const int rem = (int)(m - (long long)b * hw);
-                const int h = rem / W, w = rem - h * W;
-                if ((int)is_low_freq(h, w, H, W, bs, low) != cls) continue;
-            }
-            s += ld_any(dy, dtype, m * ldn + n);
         }
-        if (out_img) atomicAdd(&out_img[(long long)cur_b * N + n], s);
-        if (out_total) atomicAdd(&out_total[n], s);
+        seg = seg_end;
     }
 }
 

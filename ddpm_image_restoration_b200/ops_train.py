@@ -295,6 +295,21 @@ def huber_color_loss_backward(pred_noise, noise, xt, x0, color_weight, delta=1.0
     return color_preservation_loss_backward(recon, x0, upstream=color_weight, out=d)
 
 
+def pack_weight(w, fwd=None, bwd=None, fwd_ld=None, fwd_off=0, bwd_ld=None, bwd_off=0):
+    """One pass over a checkpoint-layout weight [N, Cin, kh, kw] / [N, K] (fp32) -> the forward operand [N, (kh,kw,cin)] and the
+    data-gradient operand [Cin, (kh,kw,cout)] (transposed, taps flipped) in the dtype of the outputs; leading dimensions /
+    offsets place it inside a stacked operand."""
+    N, Cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (N * Cin)
+    ref = fwd if fwd is not None else bwd
+    if bwd is not None and fwd is not None and bwd.dtype != fwd.dtype:
+        raise _lib.DdpmirError("pack_weight: fwd and bwd must share a dtype")
+    _lib.check(_lib.lib().ddpmir_pack_weight(_p(_f32(w, "w")), N, Cin, taps, _p(fwd), taps * Cin if fwd_ld is None else fwd_ld, fwd_off,
+                                             _p(bwd), taps * N if bwd_ld is None else bwd_ld, bwd_off, _code(ref.dtype), _stream()),
+               "pack_weight")
+    LAUNCHES[0] += 1
+
+
 def sumsq(x, acc):
     _lib.check(_lib.lib().ddpmir_sumsq(_p(_f32(x, "x")), x.numel(), _p(acc), _stream()), "sumsq")
     LAUNCHES[0] += 1
@@ -304,4 +319,13 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq
     _lib.check(_lib.lib().ddpmir_adamw_step(_p(p), _p(_f32(g, "g")), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
                                             float(eps), float(weight_decay), int(step), _p(grad_sumsq), float(max_norm), _stream()),
                "adamw_step")
+    LAUNCHES[0] += 1
+
+
+def adamw_multi(chunk_start, chunk_len, chunk_param, g_flat, m_flat, v_flat, lr, beta1, beta2, eps, weight_decay, step,
+                grad_sumsq=None, max_norm=1.0):
+    """clip + AdamW over every tensor of the chunk table in one launch (tables: device int64 / int32 / int64-as-pointer)."""
+    _lib.check(_lib.lib().ddpmir_adamw_multi(_p(chunk_start), _p(chunk_len), _p(chunk_param), chunk_start.numel(), _p(_f32(g_flat, "g")),
+                                             _p(m_flat), _p(v_flat), float(lr), float(beta1), float(beta2), float(eps),
+                                             float(weight_decay), int(step), _p(grad_sumsq), float(max_norm), _stream()), "adamw_multi")
     LAUNCHES[0] += 1

@@ -60,8 +60,13 @@ class Trainer:
         for k, p in self.params.items():
             self.grads[k] = self.flat_grad[off:off + p.numel()].view(p.shape)
             off += p.numel()
-        self.m = {k: torch.zeros_like(p, dtype=F32) for k, p in self.params.items()}
-        self.v = {k: torch.zeros_like(p, dtype=F32) for k, p in self.params.items()}
+        # AdamW moments: flat like the gradient (one multi-tensor launch updates everything, ops_train.adamw_multi)
+        self.flat_m, self.flat_v = torch.zeros_like(self.flat_grad), torch.zeros_like(self.flat_grad)
+        self.m, self.v, off = {}, {}, 0
+        for k, p in self.params.items():
+            self.m[k], self.v[k] = self.flat_m[off:off + p.numel()].view(p.shape), self.flat_v[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self._chunks = None
         self._norm_acc = torch.zeros((1,), dtype=torch.float64, device=dev)
         # gradient buckets for the data-parallel all-reduce: the backward finishes the blocks in reverse registration order,
         # so every finished block closes a contiguous tail [start(block), previous start) of the flat buffer
@@ -78,52 +83,67 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------------------
     def _pack(self):
         """Per-step weight packs (weights change every step): forward [N,(kh,kw,cin)] and backward (transposed,
-        tap-flipped) operands in the compute dtype."""
+        tap-flipped) operands in the compute dtype, written by ddpmir_pack_weight (one pass per checkpoint tensor) into buffers
+        that live as long as the Trainer."""
         m = self.model
         dt = torch.bfloat16 if m.precision == "bf16" else F32
-        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        sd = {k: v.detach() for k, v in m.named_parameters()}
+        bufs = self._pack_bufs if getattr(self, "_pack_dt", None) == dt else None
+        fresh = bufs is None
+        if fresh:
+            bufs, self._pack_dt = {}, dt
+        dev = next(m.parameters()).device
 
-        def cast(w):
-            w = w.contiguous().float()
-            return ops.cast_bf16(w) if dt == torch.bfloat16 else w
-        c3 = lambda w: cast(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
-        c3t = lambda w: cast(w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1))   # dgrad: [Cin, 9*Cout]
-        l1 = lambda w: cast(w.reshape(w.shape[0], -1))
-        l1t = lambda w: cast(w.reshape(w.shape[0], -1).t())
+        def buf(key, *shape):
+            if key not in bufs:
+                bufs[key] = torch.empty(shape, dtype=dt, device=dev)
+            return bufs[key]
+
+        def both(q, p, key, name):
+            """conv or linear weight -> q[key] (forward operand) and q[key + "_t"] (data-gradient operand)."""
+            w = sd[name]
+            N, Cin = w.shape[0], w.shape[1]
+            taps = w.numel() // (N * Cin)
+            q[key], q[key + "_t"] = buf((p, key), N, taps * Cin), buf((p, key, "t"), Cin, taps * N)
+            T.pack_weight(w, q[key], q[key + "_t"])
+
         P = {}
         avif = m.family == "avif"
         for p, ci, co in _BLOCKS:
             q = {}
             if ci != 3:
-                q["conv1"], q["conv1_t"] = c3(sd[f"{p}.conv1.weight"]), c3t(sd[f"{p}.conv1.weight"])
+                both(q, p, "conv1", f"{p}.conv1.weight")
                 if ci != co:
-                    q["sc"], q["sc_t"] = l1(sd[f"{p}.shortcut.weight"]), l1t(sd[f"{p}.shortcut.weight"])
-            q["conv2"], q["conv2_t"] = c3(sd[f"{p}.conv2.weight"]), c3t(sd[f"{p}.conv2.weight"])
-            q["in"], q["in_t"] = l1(sd[f"{p}.attn.in_proj_weight"]), l1t(sd[f"{p}.attn.in_proj_weight"])
-            q["out"], q["out_t"] = l1(sd[f"{p}.attn.out_proj.weight"]), l1t(sd[f"{p}.attn.out_proj.weight"])
+                    both(q, p, "sc", f"{p}.shortcut.weight")
+            both(q, p, "conv2", f"{p}.conv2.weight")
+            both(q, p, "in", f"{p}.attn.in_proj_weight")
+            both(q, p, "out", f"{p}.attn.out_proj.weight")
             f = f"{p}.freq_guide"
             if avif:
                 a = f"{f}.adaptive_transform"
-                for key, name in (("q0", f"{a}.quantization.0"), ("q2", f"{a}.quantization.2"),
-                                  ("c0", f"{f}.color_consistency.0"), ("c2", f"{f}.color_consistency.2")):
-                    q[key], q[key + "_t"] = l1(sd[name + ".weight"]), l1t(sd[name + ".weight"])
-                for key, name in (("e0", f"{f}.edge_preserve.0"), ("e2", f"{f}.edge_preserve.2")):
-                    q[key], q[key + "_t"] = c3(sd[name + ".weight"]), c3t(sd[name + ".weight"])
+                for key, name in (("q0", f"{a}.quantization.0"), ("q2", f"{a}.quantization.2"), ("c0", f"{f}.color_consistency.0"),
+                                  ("c2", f"{f}.color_consistency.2"), ("e0", f"{f}.edge_preserve.0"), ("e2", f"{f}.edge_preserve.2")):
+                    both(q, p, key, name + ".weight")
                 q["Tt"] = sd[f"{a}.transform_weights"].transpose(1, 2).contiguous().float()
             else:
-                w1 = torch.cat([sd[f"{f}.low_freq_attn.0.weight"], sd[f"{f}.high_freq_attn.0.weight"]], 0).reshape(co, co)
-                w2 = torch.cat([sd[f"{f}.low_freq_attn.2.weight"].reshape(co, co // 2), sd[f"{f}.high_freq_attn.2.weight"].reshape(co, co // 2)], 1)
-                q["g1"], q["g1_t"] = cast(w1), cast(w1.t())
-                q["g2"], q["g2_t"] = cast(w2), cast(w2.t())
+                # stacked low/high gate MLP: g1 = [W1_low; W1_high] (rows), g2 = [W2_low | W2_high] (columns), and their transposes
+                h = co // 2
+                g1, g1t, g2, g2t = buf((p, "g1"), co, co), buf((p, "g1t"), co, co), buf((p, "g2"), co, co), buf((p, "g2t"), co, co)
+                T.pack_weight(sd[f"{f}.low_freq_attn.0.weight"], g1[:h], g1t, bwd_ld=co, bwd_off=0)
+                T.pack_weight(sd[f"{f}.high_freq_attn.0.weight"], g1[h:], g1t, bwd_ld=co, bwd_off=h)
+                T.pack_weight(sd[f"{f}.low_freq_attn.2.weight"], g2, g2t[:h], fwd_ld=co, fwd_off=0)
+                T.pack_weight(sd[f"{f}.high_freq_attn.2.weight"], g2, g2t[h:], fwd_ld=co, fwd_off=h)
+                q["g1"], q["g1_t"], q["g2"], q["g2_t"] = g1, g1t, g2, g2t
                 q["g1_b"] = torch.cat([sd[f"{f}.low_freq_attn.0.bias"], sd[f"{f}.high_freq_attn.0.bias"]], 0).contiguous().float()
-            q["fo"], q["fo_t"] = c3(sd[f"{f}.conv_out.weight"]), c3t(sd[f"{f}.conv_out.weight"])
+            both(q, p, "fo", f"{f}.conv_out.weight")
             P[p] = q
         if avif:
             q = {}
-            for key, name in (("q0", "avif_layer.quantization.0"), ("q2", "avif_layer.quantization.2")):
-                q[key], q[key + "_t"] = l1(sd[name + ".weight"]), l1t(sd[name + ".weight"])
+            both(q, "tail", "q0", "avif_layer.quantization.0.weight")
+            both(q, "tail", "q2", "avif_layer.quantization.2.weight")
             q["Tt"] = sd["avif_layer.transform_weights"].transpose(1, 2).contiguous().float()
             P["tail"] = q
+        self._pack_bufs = bufs
         return P, dt
 
     def _op(self, x, dt):
@@ -513,12 +533,33 @@ class Trainer:
         self._norm_acc.zero_()
         T.sumsq(self.flat_grad, self._norm_acc)
         b1, b2 = self.betas
-        for k, p in self.params.items():
-            if k in self.unused:
-                continue
-            T.adamw_step(p.data, self.grads[k], self.m[k], self.v[k], self.lr, b1, b2, self.eps, self.wd, self.step_count,
-                         self._norm_acc, self.max_grad_norm)
+        cs, cl, cp = self._chunk_table()
+        T.adamw_multi(cs, cl, cp, self.flat_grad, self.flat_m, self.flat_v, self.lr, b1, b2, self.eps, self.wd, self.step_count,
+                      self._norm_acc, self.max_grad_norm)
         self.model._packed = None      # inference weight packs are stale now
+
+    CHUNK = 8192
+
+    def _chunk_table(self):
+        """(chunk_start, chunk_len, chunk_param) device tables of ops_train.adamw_multi: every parameter tensor cut into chunks of
+        CHUNK elements; parameters without a gradient (self.unused) are left out.  Rebuilt if a parameter's storage moved."""
+        ptrs = tuple(p.data_ptr() for p in self.params.values())
+        if self._chunks is not None and self._chunks[0] == ptrs:
+            return self._chunks[1]
+        starts, lens, pp, off = [], [], [], 0
+        for k, p in self.params.items():
+            n = p.numel()
+            if k not in self.unused:
+                if not p.is_contiguous() or p.dtype != F32:
+                    raise RuntimeError(f"parameter {k} must be a contiguous float32 tensor")
+                for c in range(0, n, self.CHUNK):
+                    starts.append(off + c); lens.append(min(self.CHUNK, n - c)); pp.append(p.data_ptr() + 4 * c)
+            off += n
+        dev = self.flat_grad.device
+        tables = (torch.tensor(starts, dtype=torch.int64, device=dev), torch.tensor(lens, dtype=torch.int32, device=dev),
+                  torch.tensor(pp, dtype=torch.int64, device=dev))
+        self._chunks = (ptrs, tables)
+        return tables
 
     def train_step(self, xt, t, x0, dropout_seed=None):
         loss = self.forward_backward(xt, t, x0, dropout_seed, overlap=True)

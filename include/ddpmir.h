@@ -375,6 +375,14 @@ int ddpmir_avgpool_pyramid_backward(const float* dpooled, int B, int H, int W, i
 int ddpmir_block_transform_wgrad(const float* x, const float* dz, const float* T, int bs, int B, int H, int W, int C, float* dT,
                                  ddpmir_stream_t stream);
 
+/* Per-step operand packing of a checkpoint-layout weight w [N, Cin, kh, kw] (fp32, taps = kh*kw = 9 or 1) for the training step
+ * (replaces the permute/flip/cat/cast chain over `state_dict` tensors; the weights change at every optimizer.step(),
+ * webp_training.py:524): fwd[n*fwd_ld + fwd_off + tap*Cin + c] = w[n,c,tap] (the [N,(kh,kw,cin)] layout of ddpmir_conv3x3 /
+ * ddpmir_gemm) and bwd[c*bwd_ld + bwd_off + (taps-1-tap)*N + n] = w[n,c,tap] (transposed, taps flipped: the data-gradient
+ * operand).  Either output may be NULL; both are `dtype` (DDPMIR_BF16 or DDPMIR_F32). */
+int ddpmir_pack_weight(const float* w, int N, int Cin, int taps, void* fwd, long long fwd_ld, long long fwd_off, void* bwd,
+                       long long bwd_ld, long long bwd_off, int dtype, ddpmir_stream_t stream);
+
 /* nn.ReLU backward from the saved OUTPUT y = relu(pre) (y in y_dtype): dpre = dy * [y > 0]. */
 int ddpmir_relu_mask_backward(const float* dy, const void* y, int y_dtype, float* dpre, int64_t n, ddpmir_stream_t stream);
 
@@ -440,6 +448,14 @@ int ddpmir_color_l1_backward(const float* pred, const float* target, int B, int 
 int ddpmir_sumsq(const float* x, int64_t n, double* acc, ddpmir_stream_t stream);
 int ddpmir_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                       float weight_decay, int step, const double* grad_sumsq, float max_norm, ddpmir_stream_t stream);
+
+/* The same fused clip + AdamW update over many tensors in ONE launch.  The gradient and both moment estimates live in flat
+ * buffers (all parameters' segments back to back); chunk c covers flat elements [chunk_start[c], chunk_start[c] + chunk_len[c])
+ * of one tensor and chunk_param[c] points at that tensor's matching elements.  The three tables are device arrays; chunks of
+ * parameters the caller wants untouched (torch skips .grad None) are simply left out. */
+int ddpmir_adamw_multi(const int64_t* chunk_start, const int32_t* chunk_len, float* const* chunk_param, int n_chunks,
+                       const float* g_flat, float* m_flat, float* v_flat, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, const double* grad_sumsq, float max_norm, ddpmir_stream_t stream);
 
 /* dtype conversion helper for weight pre-packing (fp32 -> bf16, round-to-nearest-even). */
 int ddpmir_cast_f32_to_bf16(const float* in, void* out, int64_t n, ddpmir_stream_t stream);

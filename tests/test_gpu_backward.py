@@ -283,6 +283,33 @@ def test_learned_transform_weight_gradient(ops, T, shape):
         assert torch.equal(T.relu_mask_backward(dy.cuda(), y.to(dt).cuda()).cpu(), dy * (y > 0))
 
 
+@pytest.mark.parametrize("shape", [(64, 64, 9), (128, 64, 9), (48, 40, 9), (192, 64, 1), (7, 33, 1), (1024, 512, 9)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_pack_weight(T, shape, dt):
+    """ddpmir_pack_weight against the torch expressions it replaces: [N,(kh,kw,cin)] and the transposed, tap-flipped
+    data-gradient operand; bit-exact (a cast and a permutation), incl. placement inside a stacked operand."""
+    N, Cin, taps = shape
+    w = rnd(N, Cin, 3, 3, seed=1) if taps == 9 else rnd(N, Cin, 1, 1, seed=1)
+    want_f = w.permute(0, 2, 3, 1).reshape(N, -1).to(dt)
+    want_b = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, -1).to(dt)
+    fwd = torch.full((N, taps * Cin), 7.0, dtype=dt).cuda()
+    bwd = torch.full((Cin, taps * N), 7.0, dtype=dt).cuda()
+    T.pack_weight(w.cuda(), fwd, bwd)
+    assert torch.equal(fwd.cpu(), want_f) and torch.equal(bwd.cpu(), want_b)
+    if taps == 1:       # two tensors stacked along rows (forward) / columns (transposed), as the low/high gate MLP does
+        w2 = rnd(N, Cin, 1, 1, seed=2)
+        st, stt = torch.zeros(2 * N, Cin, dtype=dt).cuda(), torch.zeros(Cin, 2 * N, dtype=dt).cuda()
+        T.pack_weight(w.cuda(), st[:N], stt, bwd_ld=2 * N, bwd_off=0)
+        T.pack_weight(w2.cuda(), st[N:], stt, bwd_ld=2 * N, bwd_off=N)
+        cat = torch.cat([w, w2], 0).reshape(2 * N, Cin)
+        assert torch.equal(st.cpu(), cat.to(dt)) and torch.equal(stt.cpu(), cat.t().contiguous().to(dt))
+        sk, skt = torch.zeros(N, 2 * Cin, dtype=dt).cuda(), torch.zeros(2 * Cin, N, dtype=dt).cuda()
+        T.pack_weight(w.cuda(), sk, skt[:Cin], fwd_ld=2 * Cin, fwd_off=0)
+        T.pack_weight(w2.cuda(), sk, skt[Cin:], fwd_ld=2 * Cin, fwd_off=Cin)
+        catk = torch.cat([w.reshape(N, Cin), w2.reshape(N, Cin)], 1)
+        assert torch.equal(sk.cpu(), catk.to(dt)) and torch.equal(skt.cpu(), catk.t().contiguous().to(dt))
+
+
 def test_frequency_aware_loss_backward(T):
     gen = g(3)
     target = torch.rand(2, 3, 32, 32, generator=gen) * 2 - 1
