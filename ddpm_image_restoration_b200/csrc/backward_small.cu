@@ -58,32 +58,53 @@ conv_input_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
     constexpr int KK = KS * KS;
     const long long total = (long long)B * H * W;
     const long long p0 = (long long)blockIdx.x * px_per_cta, p1 = min(total, p0 + px_per_cta);
-    // thread (n = tid % N-lane, pixel lane = tid / 64); N <= 64 handled per 64-wide slab
+    // thread (n lane = tid % 64, pixel lane = tid / 64); N handled per 64-wide slab.  ONE pass over the CTA's pixels with all
+    // Cin * KK accumulators in registers: dh[p, n] is read once (coalesced over n), the <= 4 x 9 normalised input samples around p
+    // are warp-uniform loads.  (The previous version made one pass per (c, tap): 27 passes, 1.2 ms at 32 x 64 x 64.)
     const int nl = threadIdx.x & 63, pl = threadIdx.x >> 6;
     __shared__ float red[4][64];
+    const int hw = H * W;
     for (int n0 = 0; n0 < N; n0 += 64) {
         const int n = n0 + nl;
-        for (int c = 0; c < Cin; ++c)
-            for (int tap = 0; tap < KK; ++tap) {
-                float s = 0.f;
-                if (n < N)
-                    for (long long p = p0 + pl; p < p1; p += 4) {
-                        const int b = (int)(p / (H * W));
-                        const int rem = (int)(p - (long long)b * H * W);
-                        const int h = rem / W + (KS == 3 ? tap / 3 - 1 : 0), w = rem % W + (KS == 3 ? tap % 3 - 1 : 0);
-                        if (h < 0 || h >= H || w < 0 || w >= W) continue;
-                        float v = x[(((long long)b * Cin + c) * H + h) * W + w];
-                        if (mean_rstd) {
-                            const float mean = mean_rstd[((long long)b * Cin + c) * 2], rstd = mean_rstd[((long long)b * Cin + c) * 2 + 1];
-                            v = fmaf((v - mean) * rstd, gamma[c], beta[c]);
-                        }
-                        s = fmaf(dh[p * N + n], v, s);
+        float acc[4][KK];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int t = 0; t < KK; ++t) acc[c][t] = 0.f;
+        if (n < N)
+            for (long long p = p0 + pl; p < p1; p += 4) {
+                const int b = (int)(p / hw);
+                const int rem = (int)(p - (long long)b * hw);
+                const int h0 = rem / W, w0 = rem - h0 * W;
+                const float g = dh[p * N + n];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= Cin) break;
+                    float sc = 1.f, sh = 0.f;
+                    if (mean_rstd) {      // gn(x) = (x - mean) * rstd * gamma + beta = x * sc + sh
+                        const float mean = mean_rstd[((long long)b * Cin + c) * 2], rstd = mean_rstd[((long long)b * Cin + c) * 2 + 1];
+                        sc = rstd * gamma[c]; sh = fmaf(-mean, sc, beta[c]);
                     }
-                red[pl][nl] = s;
+                    const float* xp = x + ((long long)b * Cin + c) * hw;
+#pragma unroll
+                    for (int t = 0; t < KK; ++t) {
+                        const int h = h0 + (KS == 3 ? t / 3 - 1 : 0), w = w0 + (KS == 3 ? t % 3 - 1 : 0);
+                        if (h < 0 || h >= H || w < 0 || w >= W) continue;
+                        acc[c][t] = fmaf(g, fmaf(xp[h * W + w], sc, sh), acc[c][t]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c >= Cin) break;
+#pragma unroll
+            for (int t = 0; t < KK; ++t) {
+                red[pl][nl] = acc[c][t];
                 __syncthreads();
-                if (pl == 0 && n < N) atomicAdd(&dw[((long long)n * Cin + c) * KK + tap], red[0][nl] + red[1][nl] + red[2][nl] + red[3][nl]);
+                if (pl == 0 && n < N) atomicAdd(&dw[((long long)n * Cin + c) * KK + t], red[0][nl] + red[1][nl] + red[2][nl] + red[3][nl]);
                 __syncthreads();
             }
+        }
     }
 }
 
@@ -165,32 +186,56 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 out_conv_bwd_weight_kernel(const T* __restrict__ a, const float* __restrict__ y, const float* __restrict__ dy, int B, int H, int W,
                            int Cin, int N, float* __restrict__ dw, float* __restrict__ dbias, int px_per_cta) {
-    // thread = (c lane 0..63, pixel lane 0..3)
+    // thread = (c lane 0..63, pixel lane 0..3).  ONE pass over the CTA's output pixels with all N * 9 accumulators in registers:
+    // dz[n] = dy (1 - y^2) at the pixel is warp-uniform, the nine shifted activation rows are coalesced over c.  (The previous
+    // version made one pass per (n, tap): 27 passes, 1.3 ms at 32 x 64 x 64.)
     const int cl = threadIdx.x & 63, pl = threadIdx.x >> 6;
     const long long total = (long long)B * H * W;
     const long long p0 = (long long)blockIdx.x * px_per_cta, p1 = min(total, p0 + px_per_cta);
     __shared__ float red[4][64];
+    const int hw = H * W;
     for (int c0 = 0; c0 < Cin; c0 += 64) {
         const int c = c0 + cl;
-        for (int n = 0; n < N; ++n)
-            for (int tap = 0; tap < 9; ++tap) {
-                float s = 0.f;
-                if (c < Cin)
-                    for (long long p = p0 + pl; p < p1; p += 4) {
-                        const int b = (int)(p / (H * W));
-                        const int rem = (int)(p - (long long)b * H * W);
-                        const int h = rem / W, ww = rem - h * W;
-                        const int hi = h + tap / 3 - 1, wi = ww + tap % 3 - 1;
-                        if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-                        const long long j = (((long long)b * N + n) * H + h) * W + ww;
+        float acc[4][9];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[n][t] = 0.f;
+        if (c < Cin)
+            for (long long p = p0 + pl; p < p1; p += 4) {
+                const int b = (int)(p / hw);
+                const int rem = (int)(p - (long long)b * hw);
+                const int h = rem / W, ww = rem - h * W;
+                float dz[4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    dz[n] = 0.f;
+                    if (n < N) {
+                        const long long j = ((long long)b * N + n) * hw + rem;
                         const float yv = y[j];
-                        s = fmaf(dy[j] * (1.f - yv * yv), to_f(a[(((long long)b * H + hi) * W + wi) * Cin + c]), s);
+                        dz[n] = dy[j] * (1.f - yv * yv);
                     }
-                red[pl][cl] = s;
+                }
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int hi = h + t / 3 - 1, wi = ww + t % 3 - 1;
+                    if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                    const float av = to_f(a[(((long long)b * H + hi) * W + wi) * Cin + c]);
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) acc[n][t] = fmaf(dz[n], av, acc[n][t]);
+                }
+            }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            if (n >= N) break;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                red[pl][cl] = acc[n][t];
                 __syncthreads();
-                if (pl == 0 && c < Cin) atomicAdd(&dw[((long long)n * Cin + c) * 9 + tap], red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]);
+                if (pl == 0 && c < Cin) atomicAdd(&dw[((long long)n * Cin + c) * 9 + t], red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl]);
                 __syncthreads();
             }
+        }
     }
     if (blockIdx.x * blockDim.x + threadIdx.x < N) { /* bias handled below by the first CTAs' threads */ }
     // bias gradient: every CTA reduces its own pixel range

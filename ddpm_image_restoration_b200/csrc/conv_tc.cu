@@ -298,7 +298,7 @@ int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, void* out, const
 }
 
 int g_num_sms = 0;
-int g_tc_variant = 0;   // 0 = auto, 1 = tiled kernel only, 2 = streaming kernel whenever legal
+int g_tc_variant = 0;   // 0 = auto, 1 = tiled kernel only, 2 = streaming kernel whenever legal, 3 = tiled kernel with the widest N tile
 
 }  // namespace
 
@@ -339,7 +339,7 @@ int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const bool stream_ok = N % 16 == 0 && N <= 256 && w_bytes <= 112 * 1024;
-    if (g_tc_variant != 1 && stream_ok && (g_tc_variant == 2 || num_tiles >= 2 * g_num_sms)) {
+    if (g_tc_variant != 1 && g_tc_variant != 3 && stream_ok && (g_tc_variant == 2 || num_tiles >= 2 * g_num_sms)) {
         const cuuint64_t K = (cuuint64_t)taps * Cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)N};
         cuuint64_t strides[1] = {K * 2};
@@ -363,7 +363,23 @@ int ddpmir_igemm_tc(int taps, const void* x, int B, int H, int W, int Cin, const
     }
     // widest N tile that divides N: per k-block a CTA moves (128 + BLOCK_N) x 128 B for 128 x BLOCK_N x 64 MACs, and the
     // L2->SM path (~42 B/clk/SM) is what bounds the tensor pipe, so wider is better
-    const int block_n = (N % 256 == 0 && taps * (Cin / BLOCK_K) > 2) ? 256 : (N % 128 == 0) ? 128 : 64;
+    // Which divisor?  A CTA's k loop is bound by its L2->SM traffic, (128 + BLOCK_N) x 128 B per k-block, and the grid runs in
+    // waves of one CTA per SM: cost ~ waves x (128 + BLOCK_N).  Large M fills the SMs at any width (widest wins, as before);
+    // the 8x8 / 16x16 levels of a 16-image micro-batch have only 8..32 pixel tiles, so narrower tiles put 2-4x more SMs to work.
+    int block_n = 64;
+    {
+        const int cand[3] = {256, 128, 64};
+        long long best = -1;
+        for (int i = 0; i < 3; ++i) {
+            const int bn = cand[i];
+            if (bn != 64 && N % bn != 0) continue;
+            if (bn == 256 && taps * (Cin / BLOCK_K) <= 2) continue;
+            const long long ctas = (long long)num_tiles * ceil_div(N, bn);
+            const long long cost = ((ctas + g_num_sms - 1) / g_num_sms) * (128 + bn);
+            if (g_tc_variant == 3) { block_n = bn; break; }        // tuning: the old rule (widest divisor)
+            if (best < 0 || cost < best) { best = cost; block_n = bn; }
+        }
+    }
     {
         const cuuint64_t K = (cuuint64_t)taps * Cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)N};

@@ -145,15 +145,19 @@ def attention_train_forward(qkv, heads):
     return out, lse
 
 
-def attention_backward(qkv, o, dout, lse, heads):
+def attention_backward(qkv, o, dout, lse, heads, dout_op=None):
+    """dout_op: optional bf16 copy of dout (the tensor-core kernel's operand); made here when the caller has none."""
     B, L, C3 = qkv.shape
     C = C3 // 3
     dqkv = torch.empty((B, L, C3), dtype=F32, device=qkv.device)
     delta = torch.empty((B, heads, L), dtype=F32, device=qkv.device)
-    dout_op = None
-    if qkv.dtype == torch.bfloat16 and L % 64 == 0 and (C // heads) <= 64:
+    if not (qkv.dtype == torch.bfloat16 and L % 64 == 0 and (C // heads) <= 64):
+        dout_op = None
+    elif dout_op is None:
         from .ops import cast_bf16
         dout_op = cast_bf16(dout.contiguous())
+    elif dout_op.dtype != torch.bfloat16 or dout_op.numel() != dout.numel():
+        raise _lib.DdpmirError("attention_backward: dout_op must be the bf16 copy of dout")
     _lib.check(_lib.lib().ddpmir_attention_backward(_p(qkv), _p(o), _code(qkv.dtype), _p(_f32(dout, "dout")), _p(dout_op), _p(lse),
                                                     _p(delta), _p(dqkv), B, L, C, heads, _stream()), "attention_backward")
     LAUNCHES[0] += 3

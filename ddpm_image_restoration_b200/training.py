@@ -447,17 +447,19 @@ class Trainer:
         dh3_op = op(dh3)
         T.wgrad(dh3_op, tp["ao"], G[f"{p}.attn.out_proj.weight"], 1)
         T.colsum(dh3, G[f"{p}.attn.out_proj.bias"])
-        dao = ops.gemm(dh3_op, W["out_t"], co, impl, out_dtype=F32)
+        # the GEMM epilogue writes the bf16 copy the tensor-core attention backward wants next to the fp32 gradient
+        bf = dt == torch.bfloat16
+        dao, dao_op = ops.gemm(dh3_op, W["out_t"], co, impl, out_dtype=F32, out2_dtype=dt) if bf else (ops.gemm(dh3_op, W["out_t"], co, impl, out_dtype=F32), None)
         dqkv = T.attention_backward(tp["qkv"].view(Bn, H * Wd, 3 * co), tp["ao"].view(Bn, H * Wd, co), dao.view(Bn, H * Wd, co),
-                                    tp["lse"], fam["heads"]).view(Bn, H, Wd, 3 * co)
+                                    tp["lse"], fam["heads"], dout_op=dao_op).view(Bn, H, Wd, 3 * co)
         dqkv_op = op(dqkv)
         T.wgrad(dqkv_op, tp["h2_op"], G[f"{p}.attn.in_proj_weight"], 1)
         T.colsum(dqkv, G[f"{p}.attn.in_proj_bias"])
-        dh2 = ops.gemm(dqkv_op, W["in_t"], co, impl, out_dtype=F32, res=dh3)
-        # h2 = conv2(dropout(gelu(gn2(h1))))
-        dh2_op = op(dh2)
+        # h2 = conv2(dropout(gelu(gn2(h1)))): dh2 only feeds GEMM-shaped consumers (weight / bias / data gradient of conv2), so in
+        # bf16 mode it is produced in the operand dtype right away
+        dh2_op = ops.gemm(dqkv_op, W["in_t"], co, impl, out_dtype=dt, res=dh3)
         T.wgrad(dh2_op, tp["a2d"], G[f"{p}.conv2.weight"], 9, oihw=True)
-        T.colsum(dh2, G[f"{p}.conv2.bias"])
+        T.colsum(dh2_op, G[f"{p}.conv2.bias"])
         da2 = ops.conv3x3(dh2_op, W["conv2_t"], co, impl, out_dtype=F32)
         if p_drop > 0:
             da2 = T.dropout(da2, p_drop, tp["dseed"])
