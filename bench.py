@@ -52,6 +52,8 @@ def parse():
                          "reference's host codec, the bit-exact device JPEG round trip "
                          "(--family jpeg only) or the opt-in DCT-domain projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off captures exactly them)")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
     ap.add_argument("--attn-lin", type=int, default=None, help="tuning: largest polynomial set of the polynomial-kernel attention tier, -1 = off")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false",
@@ -214,12 +216,16 @@ def train_line(args, dev, rank, world, steps=None):
     launches0 = ops.LAUNCHES[0]
     clocks = ClockSampler(dev.index); clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if getattr(args, "profile_range", False):
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(K):
         loss = one()
     lossv = float(loss)          # device -> host read of the step result
     e1.record()
     torch.cuda.synchronize()
+    if getattr(args, "profile_range", False):
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     clk = clocks.stop()
@@ -408,6 +414,9 @@ def run_sample_steps(job, n_steps, warm, host_io, barrier, timed_filter=None):
     if timed_filter is not None:
         ops.timing_begin(timed_filter)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = getattr(job.args, "profile_range", False) and not host_io
+    if prof:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     e0.record()
     if host_io:
@@ -415,11 +424,15 @@ def run_sample_steps(job, n_steps, warm, host_io, barrier, timed_filter=None):
         st["h2d"] += y_host.numel() * 4
     for n in range(n_steps):
         sampler.step(st, i, prefetch=not (host_io and n == n_steps - 1)); i = (i - 1) % traj
+    if not host_io:        # where the trajectory stands now: the state the per-op profile (profile_one_step) is taken on
+        job.profile_x, job.profile_i = st["x_t"], i
     if host_io:
         out_host = torch.empty(y_host.shape, dtype=torch.float32, pin_memory=True)
         out_host.copy_(st["x_t"], non_blocking=True); st["d2h"] += y_host.numel() * 4
     e1.record()
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     wall = (time.perf_counter() - t0) * 1e3
     ms = e0.elapsed_time(e1)
     timed = ops.timing_end() if timed_filter is not None else {}
@@ -436,7 +449,10 @@ def profile_one_step(job, barrier):
     import torch
     from ddpm_image_restoration_b200 import ops
     sampler = job.sampler()
-    x = job.y_host.to(job.dev)
+    # the iterate the timed run ended on (the attention tiers depend on the data: the degraded input itself would flatter them)
+    x = getattr(job, "profile_x", None)
+    x = job.y_host.to(job.dev) if x is None else x.clone()
+    i0 = getattr(job, "profile_i", job.traj - 1)
     chunks = sampler._chunks(x.shape[0])
     cfg_sigma = 0.15 if job.fam == "avif" else 0.2
 
@@ -447,12 +463,12 @@ def profile_one_step(job, barrier):
             u8 = ops.quantize_u8_hwc(x_theta)
             ops.ddrm_update(x_theta, u8, x[s_:e_], t, cfg_sigma, seed=7, step=i)
     with torch.no_grad():
-        gpu_step(job.traj - 1)
+        gpu_step(i0)
         barrier()
         ops.timing_begin(lambda name, tag: True)
         ops.TIER_LOG = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); gpu_step(job.traj - 2); e1.record()
+        e0.record(); gpu_step(i0); e1.record()
         barrier()
     tiers, ops.TIER_LOG = ops.TIER_LOG, None
     return e0.elapsed_time(e1), ops.timing_end(), tiers
@@ -579,7 +595,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     host_cores = os.cpu_count() or 1
-    codec.set_threads(args.codec_threads if args.codec_threads else max(1, host_cores // world))
+    # codec pool per rank: the rank's share of the host cores; with >= 8 cores a quarter is left to the launcher / stager threads
+    # and the encoder's own second thread (measured on 16 vCPUs: 12 threads 202 ms per step, 16 threads 208 ms)
+    share = max(1, host_cores // world)
+    codec.set_threads(args.codec_threads if args.codec_threads else (share * 3 // 4 if share >= 8 else share))
     if args.attn_expmode is not None:
         from ddpm_image_restoration_b200 import _lib
         _lib.lib().ddpmir_attention_set_expmode(args.attn_expmode)
@@ -751,7 +770,7 @@ def main():
         }
         # what bounds the step: the reference's data-consistency term is a host codec round trip of every image at every
         # timestep (avif_inference.py:438 / webp_inference.py:581); the pool's thread-time per step / its threads is a floor on
-        # the step no GPU kernel can lower.  gpu_ms_per_step = the libddpmir work of one step (profiled, rank 0).
+        # the step no GPU kernel can lower.  gpu_ms_per_step = the libddpmir work of one step, profiled on the iterate the timed run ended on (rank 0).
         cthreads = max(1, codec.pool_threads())
         floor = line["codec_cpu_ms_per_step"] / cthreads
         gpu_ms = roof["profiled_step_ms"] if roof else None

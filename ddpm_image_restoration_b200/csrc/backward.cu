@@ -166,26 +166,48 @@ __global__ void __launch_bounds__(256)
 gn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy, int HW, int C, int G, int act,
                     const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                     double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int px_per_cta) {
+    // threads = CW channel lanes (power of two >= C, <= 256) x 256 / CW pixel lanes: a 64-channel tensor keeps four pixel rows in
+    // flight per CTA instead of one (same restructuring as colsum_kernel); pixel lanes are folded in shared memory
+    __shared__ float red[4][256];
     const int b = blockIdx.y;
     const int cpg = C / G;
     const int p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
-    for (int c = threadIdx.x; c < C; c += 256) {
-        const int g = c / cpg;
-        const float mean = mean_rstd[((long long)b * G + g) * 2], rstd = mean_rstd[((long long)b * G + g) * 2 + 1];
-        const float ga = gamma[c], be = beta[c];
+    int CW = 1;
+    while (CW < C && CW < 256) CW <<= 1;
+    const int RL = 256 / CW;
+    const int cn = threadIdx.x & (CW - 1), rl = threadIdx.x / CW;
+    for (int c0 = 0; c0 < C; c0 += CW) {
+        const int c = c0 + cn;
+        const bool ok = c < C;
+        const int g = ok ? c / cpg : 0;
         float s1 = 0.f, s2 = 0.f, dg = 0.f, db = 0.f;
-        for (int p = p0; p < p1; ++p) {
-            const long long i = ((long long)b * HW + p) * C + c;
-            const float xh = (x[i] - mean) * rstd;
-            const float dyh = dy[i] * act_grad(act, fmaf(ga, xh, be));
-            dg = fmaf(dyh, xh, dg); db += dyh;
-            const float dxh = dyh * ga;
-            s1 += dxh; s2 = fmaf(dxh, xh, s2);
+        if (ok) {
+            const float mean = mean_rstd[((long long)b * G + g) * 2], rstd = mean_rstd[((long long)b * G + g) * 2 + 1];
+            const float ga = gamma[c], be = beta[c];
+            for (int p = p0 + rl; p < p1; p += RL) {
+                const long long i = ((long long)b * HW + p) * C + c;
+                const float xh = (x[i] - mean) * rstd;
+                const float dyh = dy[i] * act_grad(act, fmaf(ga, xh, be));
+                dg = fmaf(dyh, xh, dg); db += dyh;
+                const float dxh = dyh * ga;
+                s1 += dxh; s2 = fmaf(dxh, xh, s2);
+            }
         }
-        atomicAdd(&dgamma[c], dg);
-        atomicAdd(&dbeta[c], db);
-        atomicAdd(&ws[((long long)b * G + g) * 2], (double)s1);
-        atomicAdd(&ws[((long long)b * G + g) * 2 + 1], (double)s2);
+        if (RL > 1) {
+            red[0][threadIdx.x] = s1; red[1][threadIdx.x] = s2; red[2][threadIdx.x] = dg; red[3][threadIdx.x] = db;
+            __syncthreads();
+            if (rl == 0)
+                for (int l = 1; l < RL; ++l) {
+                    s1 += red[0][l * CW + cn]; s2 += red[1][l * CW + cn]; dg += red[2][l * CW + cn]; db += red[3][l * CW + cn];
+                }
+            __syncthreads();
+        }
+        if (rl == 0 && ok) {
+            atomicAdd(&dgamma[c], dg);
+            atomicAdd(&dbeta[c], db);
+            atomicAdd(&ws[((long long)b * G + g) * 2], (double)s1);
+            atomicAdd(&ws[((long long)b * G + g) * 2 + 1], (double)s2);
+        }
     }
 }
 

@@ -174,8 +174,18 @@ out_conv_tanh_kernel(const T* __restrict__ x, int B, int H, int W, int Cin, cons
         sw[i] = w[((long long)n * Cin + c) * 9 + tap];
     }
     __syncthreads();
+    // eight lanes per pixel, each lane 8 of every 64 channels: a warp reads four pixels' 128-byte channel rows per load (one
+    // full line each) instead of 32 lines with 16 bytes used -- the thread-per-pixel version was bound by LSU wavefronts
+    // (0.6 ms per 16 x 256 x 256 call for 134 MB); partial sums are folded with three shuffles
     const long long total = (long long)B * H * W;
-    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < total; px += (long long)gridDim.x * blockDim.x) {
+    const int cl = threadIdx.x & 7;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+    // the loop runs over the warp's first pixel so that all 32 lanes stay together (the shuffles below are warp-wide);
+    // out-of-range pixels of the last warp recompute the last pixel and do not store
+    for (long long base = (long long)blockIdx.x * (blockDim.x >> 3) + ((threadIdx.x >> 5) << 2); base < total; base += stride) {
+        const long long px0 = base + ((threadIdx.x & 31) >> 3);
+        const bool in = px0 < total;
+        const long long px = in ? px0 : total - 1;
         const int b = (int)(px / (H * W));
         const int rem = (int)(px - (long long)b * H * W);
         const int h = rem / W, ww = rem - h * W;
@@ -184,7 +194,7 @@ out_conv_tanh_kernel(const T* __restrict__ x, int B, int H, int W, int Cin, cons
             const int hh = h + tap / 3 - 1, w2 = ww + tap % 3 - 1;
             if (hh < 0 || hh >= H || w2 < 0 || w2 >= W) continue;
             const T* src = x + (((long long)b * H + hh) * W + w2) * Cin;
-            for (int c = 0; c < Cin; c += 8) {
+            for (int c = cl * 8; c < Cin; c += 64) {
                 Vec8<T> a;
                 a.load(src + c);
                 for (int n = 0; n < N; ++n) {
@@ -194,8 +204,15 @@ out_conv_tanh_kernel(const T* __restrict__ x, int B, int H, int W, int Cin, cons
                 }
             }
         }
-        for (int n = 0; n < N; ++n)
-            out[((long long)b * N + n) * H * W + rem] = tanhf(acc[n] + bias[n]);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+            acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+            acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+        }
+        if (in && cl == 0)
+            for (int n = 0; n < N; ++n)
+                out[((long long)b * N + n) * H * W + rem] = tanhf(acc[n] + bias[n]);
     }
 }
 
@@ -279,7 +296,7 @@ extern "C" int ddpmir_out_conv_tanh(const void* x, int dtype, int B, int H, int 
     const size_t smem = sizeof(float) * N * 9 * Cin;
     DDPMIR_CHECK_ARG(smem <= 48 * 1024, "out_conv_tanh: weights do not fit shared memory");
     const long long total = (long long)B * H * W;
-    int grid = (int)((total + 127) / 128);
+    int grid = (int)((total + 15) / 16);            // 16 pixels per 128-thread CTA and iteration (eight lanes per pixel)
     if (grid > 148 * 16) grid = 148 * 16;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DDPMIR_F32) out_conv_tanh_kernel<float><<<grid, 128, smem, st>>>((const float*)x, B, H, W, Cin, w, bias, N, out);
