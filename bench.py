@@ -595,10 +595,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     host_cores = os.cpu_count() or 1
-    # codec pool per rank: the rank's share of the host cores; with >= 8 cores a quarter is left to the launcher / stager threads
-    # and the encoder's own second thread (measured on 16 vCPUs: 12 threads 202 ms per step, 16 threads 208 ms)
-    share = max(1, host_cores // world)
-    codec.set_threads(args.codec_threads if args.codec_threads else (share * 3 // 4 if share >= 8 else share))
+    # codec pool per rank = the rank's share of the host cores.  (Leaving a quarter of them to the launcher / stager threads gained
+    # 3 % on a 16-vCPU box at N = 1 but lost 18 % on a 24-core box at N = 2: 9 instead of 12 threads per rank, 335 vs 273 ms/step.)
+    codec.set_threads(args.codec_threads if args.codec_threads else max(1, host_cores // world))
     if args.attn_expmode is not None:
         from ddpm_image_restoration_b200 import _lib
         _lib.lib().ddpmir_attention_set_expmode(args.attn_expmode)
