@@ -52,6 +52,8 @@ def parse():
                          "reference's host codec, the bit-exact device JPEG round trip "
                          "(--family jpeg only) or the opt-in DCT-domain projection (DCTProcessor.jpeg_compress, SURVEY 8f-1)")
     ap.add_argument("--attn-expmode", type=int, default=None, help="tuning: 0 = fp32 ex2, 1 = packed bf16x2 ex2")
+    ap.add_argument("--train-family", default="webp", choices=["webp", "jpeg", "avif"],
+                    help="train workload: model family (BASELINE configs[3] is webp; avif = train_epoch_ddrm_avif, avif.py:528-590)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off captures exactly them)")
     ap.add_argument("--profile-ops", action="store_true", help="tuning: print CUDA-event time per GEMM/conv/attention shape")
@@ -195,11 +197,12 @@ def train_line(args, dev, rank, world, steps=None):
     from ddpm_image_restoration_b200.training import Trainer
     Bn, res = (args.batch if args.batch != 64 else 32), (args.res if args.res != 256 else 64)
     torch.manual_seed(0)
-    model = P.WebPDiffusionModel().to(dev).set_precision("bf16")
+    tfam = getattr(args, "train_family", "webp")
+    model = {"webp": P.WebPDiffusionModel, "jpeg": P.JPEGDiffusionModel, "avif": P.AVIFDiffusionModel}[tfam]().to(dev).set_precision("bf16")
     tr = Trainer(model, seed=rank, overlap_allreduce=not args.no_overlap)
     g = torch.Generator().manual_seed(100 + rank)
     x0 = (torch.rand(Bn, 3, res, res, generator=g) * 2 - 1)
-    xt = codec.webp_compress(x0, 30).contiguous().pin_memory()
+    xt = {"webp": codec.webp_compress, "jpeg": codec.jpeg_compress, "avif": codec.avif_compress}[tfam](x0, 30).contiguous().pin_memory()
     x0 = x0.pin_memory()
     t = (torch.randint(1, 100, (Bn,), generator=g).float() / 100.0).pin_memory()
     K = steps if steps is not None else 10
@@ -244,11 +247,12 @@ def train_line(args, dev, rank, world, steps=None):
         return None
     val = world * Bn * K / (ms / 1e3)
     nparam = sum(p.numel() for p in model.parameters())
-    return {"metric": "training images/sec (webp_training.py step, 64^2)", "value": val, "unit": "images/s", "n_gpus": world,
+    script = {"webp": "webp_training.py", "jpeg": "svd.ipynb", "avif": "avif.py"}[tfam]
+    return {"metric": f"training images/sec ({script} step, {res}^2)", "value": val, "unit": "images/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"webp_training.py training step, WebP UNet {res}x{res}, batch {Bn}/GPU, "
-                                   "frequency_aware_loss, clip+AdamW, fp32 gradient all-reduce (NCCL) in " + ("one piece after" if args.no_overlap else "buckets under") + " the backward",
+            "config": {"workload": f"{script} training step, {tfam.upper()} UNet {res}x{res}, batch {Bn}/GPU, "
+                                   f"{'avif_' if tfam == 'avif' else ''}frequency_aware_loss, clip+AdamW, fp32 gradient all-reduce (NCCL) in " + ("one piece after" if args.no_overlap else "buckets under") + " the backward",
                        "allreduce_bytes": nparam * 4, "allreduce_collectives_per_step": tr.buckets.collectives / (K + Wm)},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 2 * xt.numel() * 4 + Bn * 4,
                     "d2h_bytes_per_step": 4.0 / K},

@@ -376,8 +376,11 @@ class Trainer:
             off += s * s
         c1 = ops.gemm(h3_op, W["c0"], co, impl, bias=sd[f"{f}.color_consistency.0.bias"], act=ops.ACT_RELU)
         color = ops.gemm(c1, W["c2"], co, impl, bias=sd[f"{f}.color_consistency.2.bias"], act=ops.ACT_SIGMOID, img_scale=boost[0])
-        e1 = ops.conv3x3(h3_op, W["e0"], co // 2, impl, bias=sd[f"{f}.edge_preserve.0.bias"], act=ops.ACT_RELU)
-        edge = ops.conv3x3(e1, W["e2"], co, impl, bias=sd[f"{f}.edge_preserve.2.bias"], act=ops.ACT_SIGMOID, img_scale=boost[1])
+        # hidden width C/2 = 32 at the C = 64 blocks is below the tcgen05 kernels' 64-wide K block / N tile: those two convs (and
+        # their data gradients) take the generic kernel (inference pads the hidden layer to 64 instead, models.py::prepack)
+        impl_e = ops.IMPL_SIMT if co // 2 < 64 else impl
+        e1 = ops.conv3x3(h3_op, W["e0"], co // 2, impl_e, bias=sd[f"{f}.edge_preserve.0.bias"], act=ops.ACT_RELU)
+        edge = ops.conv3x3(e1, W["e2"], co, impl_e, bias=sd[f"{f}.edge_preserve.2.bias"], act=ops.ACT_SIGMOID, img_scale=boost[1])
         tp.update(tg=tg, xt=xt, gates=gates, ms=ms, h3_op=h3_op, c1=c1, color=color, e1=e1, edge=edge)
         return ops.avif_combine(h3, xt, gates, color, edge)
 
@@ -391,12 +394,13 @@ class Trainer:
         dze_op = op(dze)
         T.wgrad(dze_op, tp["e1"], G[f"{f}.edge_preserve.2.weight"], 9, oihw=True)
         T.colsum(dze, G[f"{f}.edge_preserve.2.bias"])
-        de1 = ops.conv3x3(dze_op, W["e2_t"], co // 2, impl, out_dtype=F32)
+        impl_e = ops.IMPL_SIMT if co // 2 < 64 else impl
+        de1 = ops.conv3x3(dze_op, W["e2_t"], co // 2, impl_e, out_dtype=F32)
         dpe = T.relu_mask_backward(de1, tp["e1"])
         dpe_op = op(dpe)
         T.wgrad(dpe_op, tp["h3_op"], G[f"{f}.edge_preserve.0.weight"], 9, oihw=True)
         T.colsum(dpe, G[f"{f}.edge_preserve.0.bias"])
-        dh3 = ops.conv3x3(dpe_op, W["e0_t"], co, impl, out_dtype=F32, res=de)        # + the direct path  x + enhanced
+        dh3 = ops.conv3x3(dpe_op, W["e0_t"], co, impl_e, out_dtype=F32, res=de)      # + the direct path  x + enhanced
         # colour gate: sigmoid(1x1(relu(1x1(h3))))
         dzc_op = op(dzc)
         T.wgrad(dzc_op, tp["c1"], G[f"{f}.color_consistency.2.weight"], 1)
