@@ -673,7 +673,7 @@ def main():
     ms_per_step = sum(ms_f)
 
     # one profiled timestep (after the timed runs): every libddpmir op between CUDA events -> roofline objects
-    roof = roof_convs = roof_attn = hbm_table = None
+    roof = roof_convs = roof_attn = hbm_table = roof_top = None
     if rank == 0:
         job = jobs[-1]
         step_ms, timed, tiers = profile_one_step(job, lambda: torch.cuda.synchronize())
@@ -735,6 +735,27 @@ def main():
                             "(one multiply + half a convert per feature), the tensor pipe follows.  reference_equivalent_tflops = the "
                             "reference's 4 L^2 C FLOP / the same time")
 
+        # An attention call is a pipeline of ~15 kernels (pre-pass, per-degree state / reduce / output, quadratic tiers).  The
+        # largest SINGLE kernel of the step (first in the ncu launch list, profiles/r2_step_launches_summary.txt) is the
+        # streaming conv kernel: its group gets the same treatment, against the HBM roofline, with DRAM traffic from ncu.
+        roof_top = None
+        for (kname, ktag), kg in groups:
+            if not kname.startswith("igemm_tc_stream_kernel"):
+                continue
+            kkey = f"{kname}{list(ktag)}"
+            ktraffic, ksrc = traffic_from_profile(kkey)
+            kwork, kms = kg["work_total"] / kg["calls"], kg["ms"] / kg["calls"]
+            kach = kwork / (kms * 1e-3) / 1e9
+            roof_top = {"bound": "hbm", "kernel": kkey, "achieved": kach, "peak": pk["hbm"], "unit": "GB/s", "frac": kach / pk["hbm"],
+                        "peak_source": pk["src"] + " (copy bandwidth)", "launch_ms": kms, "launches_per_step": kg["calls"],
+                        "share_of_step": kg["ms"] / step_ms, "algorithmic_work": kwork, "traffic": ktraffic, "traffic_source": ksrc,
+                        "note": "every conv3x3 / 1x1 GEMM of this activation extent that runs on the persistent weight-resident tcgen05 "
+                                "kernel (csrc/conv_tc.cu): achieved = sum of algorithmic bytes (bf16 operand in + each output / residual / "
+                                "gate tensor once) / sum of times; launch_ms and algorithmic_work are per-launch means over launches that "
+                                "differ in K, N and epilogue tensors, `traffic` is the ncu DRAM byte count of its heaviest member (a 64->64 "
+                                "3x3 conv with fp32 residual and fp32 output, 671 MB algorithmic)"}
+            break
+
     unet_tflops = UNET_GF[jobs[0].fam] * B_total / 1e3 / (ms_per_step / 1e3) if (args.res == 256 and len(jobs) == 1) else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -763,7 +784,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": sum(s_["h2d"] for s_ in stats_e2e) / K,
                     "d2h_bytes_per_step": sum(s_["d2h"] for s_ in stats_e2e) / K,
                     "note": "DDRM sampler public API from pinned host images to pinned host result; wall clock"},
-            "gpu_launches": sum(s_["launches"] for s_ in stats_f), "clocks": clk, "roofline": roof, "roofline_convs": roof_convs,
+            "gpu_launches": sum(s_["launches"] for s_ in stats_f), "clocks": clk, "roofline": roof, "roofline_top_kernel": roof_top, "roofline_convs": roof_convs,
             "roofline_attention": roof_attn, "hbm_kernels": hbm_table, "cpu_baseline": cpu,
             "unet_tflops": unet_tflops, "unet_frac_of_bf16_sustained": (unet_tflops / pk["tf_sustained"]) if unet_tflops else None,
             "codec_wait_ms_per_step": sum(s_["codec_s"] for s_ in stats_f) * 1e3 / K,
