@@ -170,3 +170,28 @@ def test_two_rank_gloo_sharding_and_timing():
     assert [r[1] for r in res] == [2.0, 2.0]      # max over ranks
     assert [r[2] for r in res] == [10.0, 10.0]    # every unit processed exactly once
     assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 5, 5, 10)
+
+
+def test_bench_op_grouping_and_stream_kernel_rule():
+    """bench.py's per-op accounting: conv3x3 / gemm calls that the persistent streaming kernel serves are grouped by KERNEL with
+    their algorithmic bytes (HBM roofline), everything else by (op, shape) with FLOP or bytes; the dispatch rule mirrors
+    csrc/conv_tc.cu (whole weight <= 112 KB in shared memory, N % 16 == 0, N <= 256, >= 2 pixel tiles per SM)."""
+    import bench
+    full = (16, 256, 256, 64, 64, 64 * 2 + 64 * 8)           # B, H, W, K, N, bytes per pixel (bf16 in, fp32 out + fp32 residual)
+    assert bench.igemm_stream_kernel("conv3x3", full) == "igemm_tc_stream_kernel<128>"
+    assert bench.igemm_stream_kernel("gemm", (16, 256, 256, 64, 192, 0)) == "igemm_tc_stream_kernel<512>"
+    assert bench.igemm_stream_kernel("conv3x3", (16, 256, 256, 128, 64, 0)) is None      # 9 * 128 * 64 * 2 B = 147 KB of weights
+    assert bench.igemm_stream_kernel("conv3x3", (16, 8, 8, 1024, 1024, 0)) is None       # N > 256
+    assert bench.igemm_stream_kernel("gemm", (1, 64, 64, 64, 64, 0)) is None             # 32 tiles < 2 per SM
+    timed = {"conv3x3": [(0.25, full), (0.35, full)], "gemm": [(0.1, (16, 8, 8, 1024, 1024, 4096))],
+             "groupnorm_apply": [(0.05, (16, 65536, 64, 4, 2))]}
+    classes, groups = bench.summarize_ops(timed, {"hbm": 6552.3, "tf_sustained": 1373.5})
+    (name, tag), g = groups[0]
+    assert name == "igemm_tc_stream_kernel<128>" and tag == (16, 256, 256) and g["calls"] == 2 and g["kind"] == "bytes"
+    px = 16 * 256 * 256
+    assert g["work_total"] == pytest.approx(2.0 * px * full[5])
+    assert g["gbs"] == pytest.approx(2.0 * px * full[5] / 0.6e-3 / 1e9)
+    assert classes["conv3x3"]["tflops"] == pytest.approx(2 * 2.0 * px * 64 * 64 * 9 / 0.6e-3 / 1e12)
+    kinds = {k[0]: v["kind"] for k, v in groups}
+    assert kinds["gemm"] == "flops" and kinds["groupnorm_apply"] == "bytes"
+    assert bench.op_work("attention", (16, 65536, 64, 8)) == ("flops", 4.0 * 16 * 65536.0 * 65536 * 64)
